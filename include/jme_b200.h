@@ -1,0 +1,166 @@
+/*
+ * jme_b200.h - C ABI of libjme_b200.so: the B200 (sm_100a) drop-in for JMolecularEnergy's
+ * MMFF94 energy / gradient hot path.
+ *
+ * Plain C, no CUDA or torch types: every pointer is caller-owned HOST memory unless the
+ * name says "_device".  One handle = one parameterised molecule on one GPU (the current
+ * CUDA device at jme_create).  A handle is not thread-safe, like the reference's
+ * ForceField objects.  All functions return JME_OK (0) or a negative jme_status; the text
+ * of the last failure is in jme_last_error(handle) (jme_last_create_error() when no
+ * handle exists yet).  There is no CPU fallback: without a usable CUDA device jme_create
+ * fails with JME_ERR_CUDA.
+ *
+ * Reference interfaces replaced (paths under /root/reference/src/main/java/org/jme):
+ *   jme_create            <- the result of MMFF94.assignParameters, forcefield/mmff/MMFF94.java:111-219
+ *                            (atom/bond/container properties set at :117-120,:151,:160,:215-219)
+ *   jme_set_options       <- ForceField.setCutoffDistance/setDielectricConstant/setEnergyUnit,
+ *                            forcefield/ForceField.java:175,199,117
+ *   jme_set_coords        <- reading IAtom.getPoint3d() of every atom (e.g. MMFF94VdwComponent.java:136)
+ *   jme_set_coord1        <- GradientDescentMinimizer.movePoint, minimizer/GradientDescentMinimizer.java:107-115
+ *   jme_energy            <- MMFF94.calculateEnergy, forcefield/mmff/MMFF94.java:385-397 and the seven
+ *                            EnergyComponent.calculateEnergy overrides it sums (forcefield/EnergyComponent.java:55)
+ *   jme_energy_gradient   <- no counterpart: the reference has no gradient; this is
+ *                            d(jme_energy)/d(xyz)
+ *   jme_last_error        <- the unchecked exceptions of MMFF94.java:371-375 etc.
+ */
+#ifndef JME_B200_H
+#define JME_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JME_ABI_VERSION 1
+
+typedef struct jme_handle jme_handle_t;
+
+typedef enum {
+    JME_OK = 0,
+    JME_ERR_INVALID = -1,      /* bad argument (null pointer, index out of range, size mismatch) */
+    JME_ERR_CUDA = -2,         /* no device / CUDA runtime failure (text has the CUDA error) */
+    JME_ERR_NOT_ASSIGNED = -3, /* coordinates never set: "MMFF94 parameters need to be assigned first" */
+    JME_ERR_NOMEM = -4,
+    JME_ERR_UNSUPPORTED = -5
+} jme_status;
+
+/* ForceField.EnergyUnit (ForceField.java:133-160); factors 4184 / 1000 / 1 J */
+typedef enum { JME_KCAL_PER_MOL = 0, JME_KJ_PER_MOL = 1, JME_JOULE_PER_MOL = 2 } jme_energy_unit;
+
+/* Component order of MMFF94.java:98 */
+enum { JME_BOND = 0, JME_ANGLE = 1, JME_STRETCH_BEND = 2, JME_OOP = 3, JME_TORSION = 4, JME_VDW = 5, JME_ELE = 6,
+       JME_N_COMPONENTS = 7 };
+
+/* Nonbonded path selection (jme_set_path). AUTO: all-pairs tiles when cutoff <= 0 or the
+ * system is small, cell-list path otherwise. */
+typedef enum { JME_PATH_AUTO = 0, JME_PATH_ALLPAIRS = 1, JME_PATH_CELLS = 2 } jme_path;
+
+/*
+ * Everything MMFF94.assignParameters leaves on the container, flattened.  All tabulated
+ * parameters are binary32 because the reference stores them as float/Float
+ * (MMFF94Parameters.java:361-379,432-444) and widens at use; pass the floats, never
+ * re-parsed decimals.
+ */
+typedef struct {
+    int64_t n_atoms;
+    const int32_t* atom_type;   /* [n_atoms] MMFF numeric type 1..82, 87..99 ("mmff.type", MMFF94.java:117) */
+    const double*  charge;      /* [n_atoms] partial charge, atom.getCharge() (MMFF94.java:616) */
+    const uint8_t* linear;      /* [n_atoms] GeometricParameters.ideallyLinear of the atom (MMFF94.java:120) */
+
+    int32_t n_vdw_types;        /* rows of MMFF94-vdw.par for the types that occur */
+    const int32_t* vdw_type;    /* [n_vdw_types] numeric type of the row */
+    const float* vdw_alpha;     /* VdwParameters.alpha, N, A, G (MMFF94Parameters.java:368) */
+    const float* vdw_N;
+    const float* vdw_A;
+    const float* vdw_G;
+    const uint8_t* vdw_DA;      /* 0 none, 1 donor, 2 acceptor (MMFF94Parameters.java:363-365) */
+
+    int64_t n_bonds;            /* container.bonds() with StretchParameters (MMFF94.java:222-256) */
+    const int32_t* bond_i; const int32_t* bond_j;
+    const float* bond_kb; const float* bond_r0;
+
+    int64_t n_angles;           /* "mmff.angleBending" + "mmff.stretchBend" maps share keys (MMFF94.java:180-183) */
+    const int32_t* angle_i; const int32_t* angle_j; const int32_t* angle_k;   /* j is the centre */
+    const float* angle_ka; const float* angle_theta0;                         /* Float[4], Float[5] of the angle row */
+    const float* stbn_kba_ijk; const float* stbn_kba_kji;                     /* Float[4], Float[5] of the stretch-bend row */
+
+    int64_t n_oops;             /* non-null rows of "mmff.outOfPlane" (MMFF94.java:184-193) */
+    const int32_t* oop_i; const int32_t* oop_j; const int32_t* oop_k; const int32_t* oop_l;  /* j centre, l out of plane */
+    const float* oop_koop;
+
+    int64_t n_torsions;         /* "mmff.torsion" (MMFF94.java:196-210) */
+    const int32_t* tor_i; const int32_t* tor_j; const int32_t* tor_k; const int32_t* tor_l;
+    const float* tor_v1; const float* tor_v2; const float* tor_v3;
+} jme_system_t;
+
+int jme_abi_version(void);
+const char* jme_last_create_error(void);
+
+/* Marshal a parameterised molecule to the current CUDA device: SoA coordinates, charges, dense
+ * type indices, type-pair vdW table, bonded term arrays, and the nonbonded pair predicate
+ * (1-2/1-3 excluded, 1-4 flagged; MMFF94.java:162-170,1106-1140) rebuilt from the bond list. */
+int jme_create(const jme_system_t* sys, jme_handle_t** out);
+void jme_destroy(jme_handle_t* h);
+const char* jme_last_error(const jme_handle_t* h);
+
+/* cutoff <= 0 means unlimited, dielectric > 0 (ForceField.java:162-210). */
+int jme_set_options(jme_handle_t* h, double cutoff, double dielectric, int energy_unit);
+int jme_set_path(jme_handle_t* h, int path);
+
+/* Atom-row sharding for multi-GPU runs: this handle evaluates rank `rank` of `world` shares of the
+ * nonbonded rows and bonded terms; the caller sums energies and gradients over ranks (all-reduce). */
+int jme_set_shard(jme_handle_t* h, int rank, int world);
+
+/* xyz is AoS [n_atoms][3] (x0,y0,z0,x1,...) like an array of Point3d. */
+int jme_set_coords(jme_handle_t* h, const double* xyz, int64_t n_atoms);
+int jme_set_coord1(jme_handle_t* h, int64_t atom, int axis, double value);
+int jme_get_coords(jme_handle_t* h, double* xyz, int64_t n_atoms);
+
+/* total = sum of comps[0..6] in component order, each already in the selected energy unit. */
+int jme_energy(jme_handle_t* h, double* total, double comps[JME_N_COMPONENTS]);
+/* grad_xyz AoS [n_atoms][3] = dE/dx (NOT the force), same unit per Angstrom. */
+int jme_energy_gradient(jme_handle_t* h, double* total, double comps[JME_N_COMPONENTS], double* grad_xyz);
+
+/* pairs_evaluated: non-excluded pairs inside the cutoff whose vdW+ele terms were summed in the last
+ * evaluation of this shard; pairs_candidate: non-excluded pairs before the cutoff test (all-pairs
+ * path) or distance tests made (cell path). */
+int jme_pair_stats(jme_handle_t* h, uint64_t* pairs_evaluated, uint64_t* pairs_candidate);
+
+/* Test/diagnostic: the selected pair set of the last evaluation, i<j, is14 flag; returns the number
+ * of pairs through *n_pairs; fills at most `capacity` entries. */
+int jme_pair_list(jme_handle_t* h, int32_t* pair_i, int32_t* pair_j, uint8_t* is14, int64_t capacity,
+                  int64_t* n_pairs);
+
+/* ---- device-resident entry points (multi-GPU plumbing and HBM-resident benchmarking) ----
+ * All work is enqueued on `stream` (a cudaStream_t passed as void*, NULL = the handle's own stream);
+ * nothing is synchronised.  d_xyz: device AoS [n_atoms][3].  d_out: device doubles
+ * [0]=total [1..7]=components [8]=pairs evaluated (as double) [9..9+3n) gradient AoS (only when
+ * want_gradient).  This is the buffer a multi-GPU caller all-reduces. */
+int jme_set_stream(jme_handle_t* h, void* stream);
+int jme_set_coords_device(jme_handle_t* h, const double* d_xyz, int64_t n_atoms);
+int jme_eval_device(jme_handle_t* h, int want_gradient, double* d_out);
+int64_t jme_eval_out_size(const jme_handle_t* h, int want_gradient);   /* doubles */
+
+/* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
+uint64_t jme_launch_count(const jme_handle_t* h);
+
+/* FP64 FMA-pipe peak of the current device measured with a dependent-chain DFMA kernel:
+ * returns TFLOP/s (2 flop per FMA) through *tflops. */
+int jme_measure_fp64_peak(double* tflops, double* sm_clock_mhz_estimate);
+
+/* Host-side topology helpers (marshalling; MMFF94.java:158-212,1106-1140).  Two-call pattern:
+ * pass NULL outputs to get counts. */
+int jme_enumerate_terms(int64_t n_atoms, const int32_t* atom_type, const uint8_t* linear,
+                        int64_t n_bonds, const int32_t* bond_i, const int32_t* bond_j,
+                        int32_t* angles /*[n][3]*/, int64_t* n_angles,
+                        int32_t* oops /*[n][4]*/, int64_t* n_oops,
+                        int32_t* torsions /*[n][4]*/, int64_t* n_torsions);
+int jme_exclusions(int64_t n_atoms, int64_t n_bonds, const int32_t* bond_i, const int32_t* bond_j,
+                   int64_t* row_ptr /*[n_atoms+1]*/, int32_t* partner, uint8_t* is14, int64_t capacity,
+                   int64_t* n_entries);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JME_B200_H */

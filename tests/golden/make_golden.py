@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under ``tests/golden/`` from the reference's own test data.
+
+Run in the build container only (it reads ``/root/reference``, which does not exist on
+the GPU box); the JSON it writes is committed and is what the tests read.
+
+For each hand-typed molecule of the reference's MMFF94 validation suite
+(``src/test/resources/org/jme/forcefield/mmff/MMFF94_dative.mol2`` geometry,
+``MMFF94.energies`` OPTIMOL column - the same files ``MMFF94Test.java:70-90`` reads) it
+
+1. takes coordinates and bonds from the mol2 record,
+2. assigns MMFF numeric atom types BY HAND (the CDK typer is not available here) and
+   formal charges for the bare ions,
+3. looks every parameter up in the reference's ``.par`` tables (table hits only, see
+   ``jmolecularenergy_b200/builder.py``),
+4. evaluates the pure-Python restatement (``oracle/py_oracle.py``) and keeps the
+   molecule only if it reproduces the published total to 1e-5 kcal/mol.
+
+A molecule that fails step 4 is reported and skipped - that means the hand typing (or a
+needed empirical rule) is wrong, and it must not become a fixture.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from jmolecularenergy_b200.builder import parameterize            # noqa: E402
+from jmolecularenergy_b200.mmff_tables import MMFFTables, ParameterNotTabulated  # noqa: E402
+from oracle import py_oracle                                     # noqa: E402
+
+REF = "/root/reference"
+PAR_DIR = f"{REF}/src/main/resources/org/jme/forcefield/mmff"
+MOL2 = f"{REF}/src/test/resources/org/jme/forcefield/mmff/MMFF94_dative.mol2"
+ENERGIES = f"{REF}/src/test/resources/org/jme/forcefield/mmff/MMFF94.energies"
+
+WATER = {"O": 70, "H": 31}
+# name -> (type per atom by mol2 atom order | callable(symbol)->type, {atom index: formal charge})
+HAND_TYPED = {
+    # ion - water complexes: OH2=70, HOH=31, ions 87..99 (MMFF94-atom-type-equivalence.par)
+    "NAPW":   (lambda el: {"NA": 93, **WATER}[el], {"NA": 1.0}),
+    "KPW1":   (lambda el: {"K": 94, **WATER}[el], {"K": 1.0}),
+    "LIPW1":  (lambda el: {"LI": 92, **WATER}[el], {"LI": 1.0}),
+    "FMW1":   (lambda el: {"F": 89, **WATER}[el], {"F": -1.0}),
+    "CLMW1":  (lambda el: {"CL": 90, **WATER}[el], {"CL": -1.0}),
+    "BRMW1":  (lambda el: {"BR": 91, **WATER}[el], {"BR": -1.0}),
+    "CA2PW3": (lambda el: {"CA": 96, **WATER}[el], {"CA": 2.0}),
+    "MG2PW3": (lambda el: {"MG": 99, **WATER}[el], {"MG": 2.0}),
+    "ZN2PW3": (lambda el: {"ZN": 95, **WATER}[el], {"ZN": 2.0}),
+    "CU1PW1": (lambda el: {"CU": 97, **WATER}[el], {"CU": 1.0}),
+    "CU2PW3": (lambda el: {"CU": 98, **WATER}[el], {"CU": 2.0}),
+    "FE2PW3": (lambda el: {"FE": 87, **WATER}[el], {"FE": 2.0}),
+    "FE3PW3": (lambda el: {"FE": 88, **WATER}[el], {"FE": 3.0}),
+    # formaldehyde: C=O 3, O=C 7, HC 5
+    "CO01A":  (lambda el: {"C": 3, "O": 7, "H": 5}[el], {}),
+    # formic acid (mol2 order O.3, O.2, C.2, H(C), H(O)): OC=O 6, O=C 7, C=O 3, HC 5, HOCO 24
+    "KHDFRM11": ([6, 7, 3, 5, 24], {}),
+    # ammonia: NR 8, HNR 23 - pins a non-zero Wilson angle
+    "NH10A":  (lambda el: {"N": 8, "H": 23}[el], {}),
+    # hydrogen sulfide: S 15, HS 71
+    "SR01A":  (lambda el: {"S": 15, "H": 71}[el], {}),
+    # phosphine: P 26, HP 71
+    "PR01A":  (lambda el: {"P": 26, "H": 71}[el], {}),
+    # small neutral organics, typed per atom in mol2 order (torsions, sp2 out-of-plane, 1-4 pairs)
+    "HL13A":  ([11, 2, 2, 5, 5, 5], {}),                       # vinyl fluoride
+    "OH10A":  ([2, 2, 6, 5, 5, 5, 29], {}),                    # vinyl alcohol (HOCC = 29)
+    "CA04A":  ([7, 3, 3, 7, 6, 24, 5], {}),                    # glyoxylic acid
+    "CE05A":  ([2, 2, 6, 3, 7, 5, 5, 5, 5], {}),               # vinyl formate
+    "CO08A":  ([2, 1, 3, 7, 5, 2, 5, 5, 5, 5, 5], {}),         # but-3-enal
+    "IM02A":  ([3, 9, 1, 5, 5, 5, 5, 5], {}),                  # N-methylformaldehydeimine
+    "SR05A":  ([15, 15, 1, 71, 5, 5, 5], {}),                  # methyl hydrogen disulfide
+    "PR02A":  ([1, 26, 71, 71, 5, 5, 5], {}),                  # methylphosphine
+    "SI02A":  ([19, 1, 5, 5, 5, 5, 5, 5], {}),                 # methylsilane
+    "SI03A":  ([19, 1, 6, 5, 5, 5, 5, 5, 21], {}),             # methyl hydroxyl silane
+}
+
+
+def read_mol2(path):
+    """name -> dict(atoms=[(element, x, y, z, mol2_charge)], bonds=[(a, b, order_str)], line)."""
+    mols = {}
+    with open(path) as fh:
+        lines = fh.read().split("\n")
+    n = 0
+    while n < len(lines):
+        if lines[n].startswith("@<TRIPOS>MOLECULE"):
+            name = lines[n + 1].strip()
+            na, nb = (int(v) for v in lines[n + 2].split()[:2])
+            m = n
+            while not lines[m].startswith("@<TRIPOS>ATOM"):
+                m += 1
+            atoms = []
+            for row in lines[m + 1:m + 1 + na]:
+                c = row.split()
+                atoms.append((c[5].split(".")[0].upper(), float(c[2]), float(c[3]), float(c[4]), float(c[8])))
+            while not lines[m].startswith("@<TRIPOS>BOND"):
+                m += 1
+            bonds = []
+            for row in lines[m + 1:m + 1 + nb]:
+                c = row.split()
+                bonds.append((int(c[1]) - 1, int(c[2]) - 1, c[3]))
+            mols[name] = dict(atoms=atoms, bonds=bonds, line=n + 2)
+            n = m
+        n += 1
+    return mols
+
+
+def read_energies(path):
+    out = {}
+    with open(path) as fh:
+        for ln, line in enumerate(fh, 1):
+            if line.startswith("*") or not line.strip():
+                continue
+            c = line.split()
+            out[c[0]] = (float(c[1]), ln)
+    return out
+
+
+def ethanol_geometry():
+    """Staggered (anti) ethanol from textbook internal coordinates; 9 atoms C C O H H H H H H.
+    Not a reference fixture (ethanol is not in the validation suite): it is BASELINE.json's
+    config 1 input, so it has no published energy."""
+    def place(a, b, c, r, theta_deg, phi_deg):
+        # position of atom d bonded to c, angle (b,c,d)=theta, dihedral (a,b,c,d)=phi
+        th, ph = np.radians(theta_deg), np.radians(phi_deg)
+        bc = c - b
+        bc /= np.linalg.norm(bc)
+        nrm = np.cross(b - a, bc)
+        nrm /= np.linalg.norm(nrm)
+        m = np.cross(nrm, bc)
+        d2 = np.array([-r * np.cos(th), r * np.sin(th) * np.cos(ph), r * np.sin(th) * np.sin(ph)])
+        return c + d2[0] * bc + d2[1] * m + d2[2] * nrm
+    c1 = np.array([0.0, 0.0, 0.0])
+    c2 = np.array([1.52, 0.0, 0.0])
+    dummy = np.array([0.0, 1.0, 0.0])
+    o = place(dummy, c1, c2, 1.43, 109.5, 180.0)
+    h_o = place(c1, c2, o, 0.97, 108.0, 180.0)
+    h21 = place(dummy, c1, c2, 1.09, 109.5, 60.0)
+    h22 = place(dummy, c1, c2, 1.09, 109.5, -60.0)
+    h11 = place(o, c2, c1, 1.09, 109.5, 180.0)
+    h12 = place(o, c2, c1, 1.09, 109.5, 60.0)
+    h13 = place(o, c2, c1, 1.09, 109.5, -60.0)
+    xyz = np.round(np.array([c1, c2, o, h11, h12, h13, h21, h22, h_o]), 4)
+    types = [1, 1, 6, 5, 5, 5, 5, 5, 21]          # CR CR OR HC*5 HOR
+    bonds = [(0, 1), (1, 2), (0, 3), (0, 4), (0, 5), (1, 6), (1, 7), (2, 8)]
+    return xyz, types, bonds
+
+
+def _unit(v):
+    return v / np.linalg.norm(v)
+
+
+def build_chain(backbone: str):
+    """All-anti zig-zag chain from a backbone string of 'C'/'O' (e.g. 'CCCCOCC', trailing 'O' = alcohol).
+    Hydrogens complete every carbon to 4 and a terminal oxygen to 2 neighbours.  Returns
+    (xyz, types, bonds) with MMFF types CR=1, OR=6, HC=5, HOR=21.  Synthetic-system template."""
+    blen = {("C", "C"): 1.52, ("C", "O"): 1.43, ("O", "C"): 1.43}
+    ang = np.radians(110.5)
+    heavy = [np.zeros(3)]
+    # zig-zag in the xz-plane
+    direction = np.array([np.sin(ang / 2), 0.0, np.cos(ang / 2)])
+    for n in range(1, len(backbone)):
+        r = blen[(backbone[n - 1], backbone[n])]
+        d = direction * np.array([1.0, 1.0, 1.0 if n % 2 else -1.0])
+        heavy.append(heavy[-1] + r * d)
+    xyz = [h.copy() for h in heavy]
+    types = [1 if el == "C" else 6 for el in backbone]
+    bonds = [(n - 1, n) for n in range(1, len(backbone))]
+    tet = np.radians(109.47 / 2)
+    for n, el in enumerate(backbone):
+        nb = [m for m in (n - 1, n + 1) if 0 <= m < len(backbone)]
+        c = heavy[n]
+        if el == "C" and len(nb) == 2:
+            u1, u2 = _unit(heavy[nb[0]] - c), _unit(heavy[nb[1]] - c)
+            b, nrm = -_unit(u1 + u2), _unit(np.cross(u1, u2))
+            for sgn in (1, -1):
+                xyz.append(c + 1.09 * (np.cos(tet) * b + sgn * np.sin(tet) * nrm))
+                types.append(5)
+                bonds.append((n, len(xyz) - 1))
+        elif len(nb) == 1:
+            u1 = _unit(heavy[nb[0]] - c)
+            # frame: e1 in the backbone plane (xz), e2 = y
+            e2 = np.array([0.0, 1.0, 0.0])
+            e1 = _unit(np.cross(e2, u1))
+            if el == "C":
+                th = np.radians(109.47)
+                for k in range(3):
+                    phi = np.radians(60.0 + 120.0 * k)
+                    dvec = np.cos(np.pi - th) * u1 * -1 + np.sin(th) * (np.cos(phi) * e1 + np.sin(phi) * e2)
+                    xyz.append(c + 1.09 * _unit(dvec))
+                    types.append(5)
+                    bonds.append((n, len(xyz) - 1))
+            else:   # terminal hydroxyl
+                th = np.radians(108.0)
+                xyz.append(c + 0.97 * _unit(np.cos(th) * u1 + np.sin(th) * e1))
+                types.append(21)
+                bonds.append((n, len(xyz) - 1))
+    return np.round(np.array(xyz), 4), types, bonds
+
+
+def water_geometry(tables):
+    kb, r0 = tables.find_bond(31, 70, 0)
+    ka, th0 = tables.find_angle(31, 70, 31, 0)
+    r, th = float(r0), np.radians(float(th0))
+    xyz = np.array([[0.0, 0.0, 0.0], [r * np.sin(th / 2), 0.0, r * np.cos(th / 2)],
+                    [-r * np.sin(th / 2), 0.0, r * np.cos(th / 2)]])
+    return xyz, [70, 31, 31], [(0, 1), (0, 2)]
+
+
+def write_templates(tables):
+    """Single-molecule templates for the synthetic benchmark systems (jmolecularenergy_b200/systems.py):
+    parameters looked up once here so that nothing needs the .par tables at run time."""
+    out = os.path.join(ROOT, "jmolecularenergy_b200", "data")
+    os.makedirs(out, exist_ok=True)
+    lines = []
+    xyz, types, bonds = water_geometry(tables)
+    parameterize(tables, xyz, types, bonds, name="WATER", source="template: MMFF94 water, types 70/31").save(
+        os.path.join(out, "WATER.json"))
+    for name, t, q in (("NA", 93, 1.0), ("CL", 90, -1.0)):
+        parameterize(tables, [[0.0, 0.0, 0.0]], [t], [], formal=[q], name=name,
+                     source=f"template: monatomic ion type {t}").save(os.path.join(out, f"{name}.json"))
+    for name, backbone in (("DECANE", "C" * 10), ("DIGLYME_LIKE", "CCOCCOCCOCC"), ("OCTANOL", "CCCCCCCCO"),
+                           ("HEXANE", "C" * 6), ("BUTANOL", "CCCCO")):
+        xyz, types, bonds = build_chain(backbone)
+        s = parameterize(tables, xyz, types, bonds, name=name, source=f"template: all-anti chain {backbone}")
+        s.save(os.path.join(out, f"{name}.json"))
+        e = py_oracle.energy_components(s)
+        lines.append(f"TEMPLATE {name}: {s.n_atoms} atoms, {len(s.tor_i)} torsions, E={e['total']:.4f}")
+    return lines
+
+
+def main():
+    tables = MMFFTables(PAR_DIR)
+    mols = read_mol2(MOL2)
+    energies = read_energies(ENERGIES)
+    kept, report = [], []
+    for name, (typing, ion_charges) in HAND_TYPED.items():
+        m = mols[name]
+        if callable(typing):
+            types = [typing(a[0]) for a in m["atoms"]]
+        else:
+            types = list(typing)
+        formal = [ion_charges.get(a[0], 0.0) for a in m["atoms"]]
+        xyz = [[a[1], a[2], a[3]] for a in m["atoms"]]
+        bonds = [(a, b) for a, b, _ in m["bonds"]]
+        orders = [{"1": 1, "2": 2, "3": 3, "am": 1, "ar": 1}[o] for _, _, o in m["bonds"]]
+        expected, eline = energies[name]
+        src = (f"MMFF94_dative.mol2:{m['line']} / MMFF94.energies:{eline} (OPTIMOL); "
+               f"hand-assigned types {types}")
+        try:
+            s = parameterize(tables, xyz, types, bonds, formal, orders, name=name,
+                             expected_energy=expected, source=src)
+        except ParameterNotTabulated as exc:
+            report.append(f"SKIP {name}: needs an empirical rule ({exc})")
+            continue
+        got = py_oracle.energy_components(s)
+        ok = abs(got["total"] - expected) <= 1e-5
+        # mol2 USER_CHARGES are printed to 4 decimals: the bci charges must round to them
+        qok = np.allclose(s.charge, [a[4] for a in m["atoms"]], atol=5.1e-5)
+        report.append(f"{'KEEP' if ok and qok else 'FAIL'} {name}: E={got['total']:.6f} "
+                      f"published={expected:.5f} diff={got['total'] - expected:+.2e} charges_ok={qok}")
+        if ok and qok:
+            s.save(os.path.join(HERE, f"{name}.json"))
+            kept.append(name)
+    # ethanol: config-1 input, no published value
+    xyz, types, bonds = ethanol_geometry()
+    s = parameterize(tables, xyz, types, bonds, name="ETHANOL",
+                     source="built from internal coordinates by tests/golden/make_golden.py; "
+                            "BASELINE.json config 1; no published energy")
+    s.save(os.path.join(HERE, "ETHANOL.json"))
+    os.makedirs(os.path.join(ROOT, "jmolecularenergy_b200", "data"), exist_ok=True)
+    s.save(os.path.join(ROOT, "jmolecularenergy_b200", "data", "ETHANOL.json"))
+    report.append(f"INFO ETHANOL: E={py_oracle.energy_components(s)['total']:.6f} "
+                  f"terms: {len(s.bond_i)} bonds {len(s.angle_i)} angles {len(s.oop_i)} oop "
+                  f"{len(s.tor_i)} torsions")
+    with open(os.path.join(HERE, "MANIFEST.json"), "w") as fh:
+        json.dump({"pinned": kept, "unpinned": ["ETHANOL"]}, fh, indent=1)
+        fh.write("\n")
+    report += write_templates(tables)
+    print("\n".join(report))
+
+
+if __name__ == "__main__":
+    main()
