@@ -1,0 +1,713 @@
+// jme_api.cu - the C ABI of include/jme_b200.h: handle, marshalling to device SoA buffers, launch
+// plans and the evaluation sequence.  No CPU fallback: every entry point that computes needs a CUDA
+// device and fails with JME_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/jme_b200.h"
+#include "jme_cells.cuh"
+#include "jme_host.hpp"
+#include "jme_kernels.cuh"
+
+using namespace jme;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+const double kUnitToJoule[3] = {4184.0, 1000.0, 1.0};   // ForceField.java:135-137
+
+struct DeviceAllocs {
+    std::vector<void*> ptrs;
+    ~DeviceAllocs() { for (void* p : ptrs) cudaFree(p); }
+};
+
+}  // namespace
+
+struct jme_handle {
+    HostSystem hs;
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+
+    double cutoff = 0, dielectric = 1;
+    int unit = JME_KCAL_PER_MOL;
+    int path = JME_PATH_AUTO;
+    int rank = 0, world = 1;
+    bool coords_set = false;
+    bool plan_dirty = true;
+    int active_path = JME_PATH_ALLPAIRS;
+
+    DeviceAllocs mem;
+    DeviceSystem ds{};
+    BondedTerms bt{};
+    double *d_x = nullptr, *d_y = nullptr, *d_z = nullptr, *d_q = nullptr;
+    int* d_type = nullptr;
+    PairConst* d_table = nullptr;
+    double* d_xyz_stage = nullptr;
+
+    // all-pairs plan
+    std::vector<ApItem> items;
+    ApItem* d_items = nullptr;
+    int* d_tile_mask = nullptr;
+    TileMask* d_masks = nullptr;
+    int tiles_per_item = 1, n_chunks = 1, n_slots = 0;
+    int item_begin = 0, item_end = 0;
+    double* d_gpart = nullptr;
+    size_t gpart_bytes = 0;
+    double* d_epart = nullptr;
+    unsigned long long* d_cpart = nullptr;
+    int n_epart = 0;
+
+    // bonded plan
+    double* d_slots = nullptr;
+    long long *d_slot_ptr = nullptr, *d_slot_idx = nullptr;
+    double* d_bpart = nullptr;
+    int n_bpart = 0;
+    long long term_begin = 0, term_end = 0, slot_lo = 0, slot_hi = 0;
+
+    // cell path
+    CellPlan cells;
+
+    double* d_out = nullptr;
+    double* h_out = nullptr;   // pinned header
+    uint64_t last_pairs = 0, last_cand = 0;
+};
+
+namespace {
+
+#define JME_CUDA(h, call)                                                                        \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                       \
+            return JME_ERR_CUDA;                                                                 \
+        }                                                                                        \
+    } while (0)
+
+template <class T>
+int dev_alloc(jme_handle* h, T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+    if (e != cudaSuccess) {
+        h->err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+        return e == cudaErrorMemoryAllocation ? JME_ERR_NOMEM : JME_ERR_CUDA;
+    }
+    h->mem.ptrs.push_back(q);
+    *p = static_cast<T*>(q);
+    return JME_OK;
+}
+
+template <class T>
+int dev_upload(jme_handle* h, T** p, const std::vector<T>& v) {
+    int rc = dev_alloc(h, p, v.size());
+    if (rc) return rc;
+    if (!v.empty()) JME_CUDA(h, cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return JME_OK;
+}
+
+void dev_free(jme_handle* h, void* p) {
+    if (!p) return;
+    auto& v = h->mem.ptrs;
+    auto it = std::find(v.begin(), v.end(), p);
+    if (it != v.end()) v.erase(it);
+    cudaFree(p);
+}
+
+int fail(jme_handle* h, int code, const std::string& msg) {
+    h->err = msg;
+    return code;
+}
+
+// ---- all-pairs plan -------------------------------------------------------------------------
+// Circulant decomposition of the block-pair triangle: row I owns the tiles (I, (I+d) mod nB) for
+// d = 0 .. H(I); every unordered block pair appears exactly once and every row has the same length
+// (+-1), so rows - and ranks owning contiguous item ranges - are balanced.
+inline int half_ring(int nB, int I) {
+    const int full = (nB - 1) / 2;
+    return full + ((nB % 2 == 0 && I < nB / 2) ? 1 : 0);
+}
+
+int build_allpairs_plan(jme_handle* h) {
+    const HostSystem& hs = h->hs;
+    const int nB = h->ds.n_blocks;
+    const int n = (int)hs.n;
+    long long total_tiles = 0;
+    for (int I = 0; I < nB; ++I) total_tiles += half_ring(nB, I) + 1;
+    if (total_tiles > (1ll << 30)) return fail(h, JME_ERR_UNSUPPORTED, "system too large for the all-pairs path; set a cutoff to use the cell path");
+    // enough items to fill 148 SMs x 16 resident warps a few times over, but >= 1 tile each
+    long long tpi = total_tiles / (148ll * 16 * 4);
+    tpi = std::max(1ll, std::min(32ll, tpi));
+    h->tiles_per_item = (int)tpi;
+    const int max_row = (nB - 1) / 2 + 1 + 1;
+    h->n_chunks = (max_row + (int)tpi - 1) / (int)tpi;
+    h->n_slots = nB + h->n_chunks;
+    const size_t gpart_bytes = (size_t)h->n_slots * 3 * h->ds.n_pad * sizeof(double);
+    if (gpart_bytes > (size_t)96 << 30) return fail(h, JME_ERR_UNSUPPORTED, "all-pairs partial-gradient buffer would exceed 96 GiB; set a cutoff to use the cell path");
+
+    h->items.clear();
+    std::vector<int> row_first_item(nB + 1, 0);
+    int tile_ofs = 0;
+    for (int I = 0; I < nB; ++I) {
+        row_first_item[I] = (int)h->items.size();
+        const int len = half_ring(nB, I) + 1;
+        for (int d0 = 0; d0 < len; d0 += (int)tpi) {
+            ApItem it{I, d0, std::min((int)tpi, len - d0), tile_ofs};
+            tile_ofs += it.nd;
+            h->items.push_back(it);
+        }
+    }
+    row_first_item[nB] = (int)h->items.size();
+
+    // tile masks
+    std::vector<int> tile_mask((size_t)total_tiles, -1);
+    std::vector<TileMask> masks;
+    auto tile_index = [&](int I, int d) {
+        const ApItem& it = h->items[row_first_item[I] + d / (int)tpi];
+        return it.tile_ofs + (d - it.d0);
+    };
+    auto mask_of = [&](int I, int d) -> TileMask& {
+        int& m = tile_mask[tile_index(I, d)];
+        if (m < 0) {
+            m = (int)masks.size();
+            masks.emplace_back();
+            std::memset(&masks.back(), 0, sizeof(TileMask));
+        }
+        return masks[m];
+    };
+    // which row owns the block pair {A, B}, and at which offset
+    auto owner = [&](int A, int B, int& I, int& d) {
+        const int d1 = (B - A + nB) % nB, d2 = nB - d1;
+        if (d1 < d2 || (d1 == d2 && A < B)) { I = A; d = d1; } else { I = B; d = d2; }
+    };
+    for (int64_t i = 0; i < n; ++i)
+        for (int64_t e = hs.excl_ptr[i]; e < hs.excl_ptr[i + 1]; ++e) {
+            const uint32_t v = hs.excl_ent[e];
+            const int64_t j = v & ~kFlag14;
+            if (j <= i) continue;
+            const bool is14 = (v & kFlag14) != 0;
+            const int A = (int)(i / kTile), B = (int)(j / kTile), li = (int)(i % kTile), lj = (int)(j % kTile);
+            if (A == B) {
+                TileMask& m = mask_of(A, 0);
+                // the diagonal tile visits an unordered pair from one of its two lanes: mark both
+                if (is14) { m.f14[li] |= 1u << lj; m.f14[lj] |= 1u << li; }
+                else { m.excl[li] |= 1u << lj; m.excl[lj] |= 1u << li; }
+            } else {
+                int I, d;
+                owner(A, B, I, d);
+                TileMask& m = mask_of(I, d);
+                const int row = (I == A) ? li : lj, bit = (I == A) ? lj : li;
+                if (is14) m.f14[row] |= 1u << bit; else m.excl[row] |= 1u << bit;
+            }
+        }
+    if (h->ds.n_pad > n) {
+        // padding atoms of the last block never interact
+        const int L = nB - 1, valid = n - L * kTile;
+        const uint32_t pad_bits = valid >= 32 ? 0u : (0xffffffffu << valid);
+        for (int I = 0; I < nB; ++I) {
+            const int len = half_ring(nB, I) + 1;
+            for (int d = 0; d < len; ++d) {
+                const int J = (I + d) % nB;
+                if (I != L && J != L) continue;
+                TileMask& m = mask_of(I, d);
+                for (int r = 0; r < 32; ++r) {
+                    if (I == L && r >= valid) m.excl[r] = 0xffffffffu;
+                    if (J == L) m.excl[r] |= pad_bits;
+                }
+            }
+        }
+    }
+
+    dev_free(h, h->d_items); dev_free(h, h->d_tile_mask); dev_free(h, h->d_masks);
+    dev_free(h, h->d_gpart); dev_free(h, h->d_epart); dev_free(h, h->d_cpart);
+    int rc;
+    if ((rc = dev_upload(h, &h->d_items, h->items))) return rc;
+    if ((rc = dev_upload(h, &h->d_tile_mask, tile_mask))) return rc;
+    if ((rc = dev_upload(h, &h->d_masks, masks))) return rc;
+    if ((rc = dev_alloc(h, &h->d_gpart, gpart_bytes / sizeof(double)))) return rc;
+    h->gpart_bytes = gpart_bytes;
+    JME_CUDA(h, cudaMemsetAsync(h->d_gpart, 0, gpart_bytes, h->stream));
+    h->n_epart = (int)h->items.size();
+    if ((rc = dev_alloc(h, &h->d_epart, 2 * (size_t)h->n_epart))) return rc;
+    if ((rc = dev_alloc(h, &h->d_cpart, 2 * (size_t)h->n_epart))) return rc;
+    JME_CUDA(h, cudaMemsetAsync(h->d_epart, 0, 2 * (size_t)h->n_epart * sizeof(double), h->stream));
+    JME_CUDA(h, cudaMemsetAsync(h->d_cpart, 0, 2 * (size_t)h->n_epart * sizeof(unsigned long long), h->stream));
+    const long long ni = (long long)h->items.size();
+    h->item_begin = (int)(ni * h->rank / h->world);
+    h->item_end = (int)(ni * (h->rank + 1) / h->world);
+    return JME_OK;
+}
+
+// ---- bonded plan ----------------------------------------------------------------------------
+int build_bonded_plan(jme_handle* h) {
+    const HostSystem& hs = h->hs;
+    const long long nb = h->bt.n_bond, na = h->bt.n_angle, no = h->bt.n_oop, nt = h->bt.n_tor;
+    const long long terms = nb + na + no + nt;
+    auto slot_of_term = [&](long long t) -> long long {
+        if (t <= nb) return 2 * t;
+        t -= nb;
+        if (t <= na) return 2 * nb + 3 * t;
+        t -= na;
+        if (t <= no) return 2 * nb + 3 * na + 4 * t;
+        t -= no;
+        return 2 * nb + 3 * na + 4 * no + 4 * t;
+    };
+    h->term_begin = terms * h->rank / h->world;
+    h->term_end = terms * (h->rank + 1) / h->world;
+    h->slot_lo = slot_of_term(h->term_begin);
+    h->slot_hi = slot_of_term(h->term_end);
+    h->n_bpart = (int)((h->term_end - h->term_begin + kBondedThreads - 1) / kBondedThreads);
+    if (h->d_slots == nullptr) {
+        const long long n_slots = slot_of_term(terms);
+        // CSR atom -> slots, ascending slot id
+        std::vector<long long> ptr(hs.n + 1, 0), idx((size_t)n_slots);
+        auto for_each_slot = [&](auto&& fn) {
+            for (long long b = 0; b < nb; ++b) for (int c = 0; c < 2; ++c) fn(hs.bond_at[2 * b + c], 2 * b + c);
+            for (long long a = 0; a < na; ++a) for (int c = 0; c < 3; ++c) fn(hs.angle_at[3 * a + c], 2 * nb + 3 * a + c);
+            for (long long o = 0; o < no; ++o) for (int c = 0; c < 4; ++c) fn(hs.oop_at[4 * o + c], 2 * nb + 3 * na + 4 * o + c);
+            for (long long t = 0; t < nt; ++t) for (int c = 0; c < 4; ++c) fn(hs.tor_at[4 * t + c], 2 * nb + 3 * na + 4 * no + 4 * t + c);
+        };
+        for_each_slot([&](int atom, long long) { ++ptr[atom + 1]; });
+        for (int64_t a = 0; a < hs.n; ++a) ptr[a + 1] += ptr[a];
+        std::vector<long long> fill(ptr.begin(), ptr.end() - 1);
+        for_each_slot([&](int atom, long long s) { idx[fill[atom]++] = s; });
+        int rc;
+        if ((rc = dev_alloc(h, &h->d_slots, 3 * (size_t)n_slots))) return rc;
+        if ((rc = dev_upload(h, &h->d_slot_ptr, ptr))) return rc;
+        if ((rc = dev_upload(h, &h->d_slot_idx, idx))) return rc;
+    }
+    dev_free(h, h->d_bpart);
+    return dev_alloc(h, &h->d_bpart, 5 * (size_t)std::max(1, h->n_bpart));
+}
+
+int choose_path(const jme_handle* h) {
+    if (h->path == JME_PATH_ALLPAIRS) return JME_PATH_ALLPAIRS;
+    if (h->path == JME_PATH_CELLS) return JME_PATH_CELLS;
+    // AUTO: the cell path pays off once the cutoff sphere holds a small fraction of the atoms
+    if (h->cutoff > 0 && h->hs.n >= 6000) return JME_PATH_CELLS;
+    return JME_PATH_ALLPAIRS;
+}
+
+int ensure_plan(jme_handle* h) {
+    if (!h->plan_dirty) return JME_OK;
+    int rc;
+    const int p = choose_path(h);
+    if (p == JME_PATH_CELLS && !(h->cutoff > 0)) return fail(h, JME_ERR_INVALID, "the cell path needs a cutoff > 0");
+    if (p == JME_PATH_ALLPAIRS) {
+        if ((rc = build_allpairs_plan(h))) return rc;
+    } else {
+        if ((rc = build_cell_plan(h->cells, h->hs, h->ds, h->cutoff, h->rank, h->world, h->err))) return rc;
+        for (void* q : h->cells.take_new_allocs()) h->mem.ptrs.push_back(q);
+    }
+    if ((rc = build_bonded_plan(h))) return rc;
+    h->active_path = p;
+    h->ds.r2_max = h->cutoff > 0 ? cutoff_r2_threshold(h->cutoff) : 0.0;
+    h->ds.ele_scale = kEleC / h->dielectric;
+    h->plan_dirty = false;
+    return JME_OK;
+}
+
+size_t ap_smem_bytes(const DeviceSystem& ds) {
+    return (size_t)ds.n_types * ds.n_types * sizeof(PairConst) + kApWarps * (4 * 32 + 16) * sizeof(double);
+}
+
+template <bool GRAD, bool CUTOFF>
+int launch_ap(jme_handle* h) {
+    const int n_items = h->item_end - h->item_begin;
+    if (n_items <= 0) return JME_OK;
+    const size_t smem = ap_smem_bytes(h->ds);
+    auto kern = ap_kernel<GRAD, CUTOFF>;
+    if (smem > 48 * 1024) JME_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (n_items + kApWarps - 1) / kApWarps;
+    kern<<<grid, kApThreads, smem, h->stream>>>(h->ds, h->d_items, h->item_begin, h->item_end, h->d_tile_mask, h->d_masks,
+                                                h->d_gpart, h->ds.n_blocks, h->tiles_per_item, h->d_epart, h->d_cpart);
+    ++h->launches;
+    JME_CUDA(h, cudaGetLastError());
+    return JME_OK;
+}
+
+// Enqueue one evaluation; results land in h->d_out (or d_out_user).
+int enqueue_eval(jme_handle* h, bool grad, double* d_out_user) {
+    int rc;
+    if (!h->coords_set) return fail(h, JME_ERR_NOT_ASSIGNED, "MMFF94 parameters need to be assigned first (no coordinates set)");
+    if ((rc = ensure_plan(h))) return rc;
+    const bool cut = h->cutoff > 0;
+    ReduceArgs A{};
+    A.n = h->ds.n; A.n_pad = h->ds.n_pad;
+    if (h->active_path == JME_PATH_ALLPAIRS) {
+        if (grad) rc = cut ? launch_ap<true, true>(h) : launch_ap<true, false>(h);
+        else rc = cut ? launch_ap<false, true>(h) : launch_ap<false, false>(h);
+        if (rc) return rc;
+        A.gpart = h->d_gpart; A.n_slots = h->n_slots; A.direct = nullptr;
+        A.epart = h->d_epart; A.cpart = h->d_cpart; A.n_epart = h->n_epart;
+    } else {
+        if ((rc = run_cell_path(h->cells, h->ds, grad, h->stream, h->launches, h->err))) return rc;
+        A.gpart = nullptr; A.n_slots = 0; A.direct = h->cells.d_grad;
+        A.epart = h->cells.d_epart; A.cpart = h->cells.d_cpart; A.n_epart = h->cells.n_epart;
+    }
+    const long long n_terms = h->term_end - h->term_begin;
+    if (n_terms > 0) {
+        if (grad) bonded_kernel<true><<<h->n_bpart, kBondedThreads, 0, h->stream>>>(h->ds, h->bt, h->term_begin, h->term_end, h->d_slots, h->d_bpart);
+        else bonded_kernel<false><<<h->n_bpart, kBondedThreads, 0, h->stream>>>(h->ds, h->bt, h->term_begin, h->term_end, h->d_slots, h->d_bpart);
+        ++h->launches;
+        JME_CUDA(h, cudaGetLastError());
+    }
+    A.slots = h->d_slots; A.slot_ptr = h->d_slot_ptr; A.slot_idx = h->d_slot_idx;
+    A.slot_lo = h->slot_lo; A.slot_hi = h->slot_hi;
+    A.bpart = h->d_bpart; A.n_bpart = n_terms > 0 ? h->n_bpart : 0;
+    A.unit_num = h->unit == JME_KCAL_PER_MOL ? 1.0 : kUnitToJoule[JME_KCAL_PER_MOL];
+    A.unit_den = h->unit == JME_KCAL_PER_MOL ? 1.0 : kUnitToJoule[h->unit];
+    A.want_grad = grad ? 1 : 0;
+    A.out = d_out_user ? d_out_user : h->d_out;
+    const int grid = grad ? (h->ds.n + 31) / 32 + 1 : 1;
+    reduce_kernel<<<grid, kReduceWarps * 32, 0, h->stream>>>(A);
+    ++h->launches;
+    JME_CUDA(h, cudaGetLastError());
+    return JME_OK;
+}
+
+int finish_host(jme_handle* h, bool grad, double* total, double* comps, double* grad_xyz) {
+    JME_CUDA(h, cudaMemcpyAsync(h->h_out, h->d_out, kOutHeader * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (grad && grad_xyz && h->hs.n > 0)
+        JME_CUDA(h, cudaMemcpyAsync(grad_xyz, h->d_out + kOutHeader, 3 * (size_t)h->hs.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    JME_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (total) *total = h->h_out[0];
+    if (comps) for (int c = 0; c < JME_N_COMPONENTS; ++c) comps[c] = h->h_out[1 + c];
+    h->last_pairs = (uint64_t)h->h_out[8];
+    h->last_cand = (uint64_t)h->h_out[9];
+    return JME_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int jme_abi_version(void) { return JME_ABI_VERSION; }
+const char* jme_last_create_error(void) { return g_create_error.c_str(); }
+const char* jme_last_error(const jme_handle_t* h) { return h ? h->err.c_str() : "null handle"; }
+uint64_t jme_launch_count(const jme_handle_t* h) { return h ? h->launches : 0; }
+
+int jme_create(const jme_system_t* sys, jme_handle_t** out) {
+    if (!out) { g_create_error = "null output pointer"; return JME_ERR_INVALID; }
+    *out = nullptr;
+    jme_handle* h = new (std::nothrow) jme_handle();
+    if (!h) { g_create_error = "out of host memory"; return JME_ERR_NOMEM; }
+    auto bail = [&](int code) { g_create_error = h->err; delete h; return code; };
+    std::string e = build_host_system(sys, h->hs);
+    if (!e.empty()) { h->err = e; return bail(JME_ERR_INVALID); }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        h->err = std::string("no CUDA device: ") + (ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0") +
+                 " (libjme_b200 has no CPU fallback)";
+        return bail(JME_ERR_CUDA);
+    }
+    if (cudaGetDevice(&h->device) != cudaSuccess) { h->err = "cudaGetDevice failed"; return bail(JME_ERR_CUDA); }
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(JME_ERR_CUDA); }
+    h->stream = h->own_stream;
+
+    const HostSystem& hs = h->hs;
+    const int n = (int)hs.n;
+    const int n_pad = std::max(kTile, (n + kTile - 1) / kTile * kTile);
+    int rc;
+    auto alloc_zero = [&](double** p, size_t cnt) -> int {
+        int r = dev_alloc(h, p, cnt);
+        if (r) return r;
+        return cudaMemset(*p, 0, cnt * sizeof(double)) == cudaSuccess ? (int)JME_OK : (int)JME_ERR_CUDA;
+    };
+    if ((rc = alloc_zero(&h->d_x, n_pad)) || (rc = alloc_zero(&h->d_y, n_pad)) || (rc = alloc_zero(&h->d_z, n_pad)) ||
+        (rc = alloc_zero(&h->d_q, n_pad)))
+        return bail(rc);
+    if ((rc = dev_alloc(h, &h->d_type, n_pad))) return bail(rc);
+    if (cudaMemset(h->d_type, 0, n_pad * sizeof(int)) != cudaSuccess) { h->err = "cudaMemset failed"; return bail(JME_ERR_CUDA); }
+    if (n > 0) {
+        if (cudaMemcpy(h->d_q, hs.charge.data(), n * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(h->d_type, hs.type_idx.data(), n * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+            h->err = "upload of per-atom data failed";
+            return bail(JME_ERR_CUDA);
+        }
+    }
+    // a table with at least one entry even for an empty system
+    std::vector<PairConst> table = hs.pair_table;
+    if (table.empty()) table.push_back(PairConst{0, 1, 0, 1});
+    if ((rc = dev_upload(h, &h->d_table, table))) return bail(rc);
+    if ((rc = dev_alloc(h, &h->d_xyz_stage, 3 * (size_t)std::max(1, n)))) return bail(rc);
+    if ((rc = dev_alloc(h, &h->d_out, kOutHeader + 3 * (size_t)std::max(1, n)))) return bail(rc);
+    if (cudaMallocHost(&h->h_out, kOutHeader * sizeof(double)) != cudaSuccess) { h->err = "cudaMallocHost failed"; return bail(JME_ERR_CUDA); }
+
+    h->ds.n = n; h->ds.n_pad = n_pad; h->ds.n_blocks = n_pad / kTile; h->ds.n_types = std::max(1, hs.n_types);
+    h->ds.x = h->d_x; h->ds.y = h->d_y; h->ds.z = h->d_z; h->ds.q = h->d_q; h->ds.type = h->d_type; h->ds.table = h->d_table;
+    h->ds.r2_max = 0; h->ds.ele_scale = kEleC;
+
+    // bonded arrays
+    int* p_i; double* p_d; unsigned char* p_u;
+    h->bt.n_bond = (int)(hs.bond_par.size() / 2); h->bt.n_angle = (int)hs.angle_linear.size();
+    h->bt.n_oop = (int)hs.oop_par.size(); h->bt.n_tor = (int)(hs.tor_par.size() / 3);
+    if ((rc = dev_upload(h, &p_i, hs.bond_at))) return bail(rc); h->bt.bond_at = p_i;
+    if ((rc = dev_upload(h, &p_d, hs.bond_par))) return bail(rc); h->bt.bond_par = p_d;
+    if ((rc = dev_upload(h, &p_i, hs.angle_at))) return bail(rc); h->bt.angle_at = p_i;
+    if ((rc = dev_upload(h, &p_d, hs.angle_par))) return bail(rc); h->bt.angle_par = p_d;
+    if ((rc = dev_upload(h, &p_u, hs.angle_linear))) return bail(rc); h->bt.angle_linear = p_u;
+    if ((rc = dev_upload(h, &p_i, hs.oop_at))) return bail(rc); h->bt.oop_at = p_i;
+    if ((rc = dev_upload(h, &p_d, hs.oop_par))) return bail(rc); h->bt.oop_par = p_d;
+    if ((rc = dev_upload(h, &p_i, hs.tor_at))) return bail(rc); h->bt.tor_at = p_i;
+    if ((rc = dev_upload(h, &p_d, hs.tor_par))) return bail(rc); h->bt.tor_par = p_d;
+    *out = h;
+    return JME_OK;
+}
+
+void jme_destroy(jme_handle_t* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    delete h;
+}
+
+int jme_set_options(jme_handle_t* h, double cutoff, double dielectric, int energy_unit) {
+    if (!h) return JME_ERR_INVALID;
+    if (!(dielectric > 0) || std::isnan(cutoff) || std::isinf(cutoff)) return fail(h, JME_ERR_INVALID, "dielectric must be > 0 and cutoff finite");
+    if (energy_unit < 0 || energy_unit > 2) return fail(h, JME_ERR_INVALID, "unknown energy unit");
+    if (cutoff < 0) cutoff = 0;     // ForceField.java:175: only cutoff > 0 limits the interaction
+    if (cutoff != h->cutoff) h->plan_dirty = true;
+    h->cutoff = cutoff;
+    h->dielectric = dielectric;
+    h->unit = energy_unit;
+    h->ds.r2_max = cutoff > 0 ? cutoff_r2_threshold(cutoff) : 0.0;
+    h->ds.ele_scale = kEleC / dielectric;
+    return JME_OK;
+}
+
+int jme_set_path(jme_handle_t* h, int path) {
+    if (!h || path < 0 || path > 2) return JME_ERR_INVALID;
+    if (path != h->path) h->plan_dirty = true;
+    h->path = path;
+    return JME_OK;
+}
+
+int jme_set_shard(jme_handle_t* h, int rank, int world) {
+    if (!h) return JME_ERR_INVALID;
+    if (world < 1 || rank < 0 || rank >= world) return fail(h, JME_ERR_INVALID, "need 0 <= rank < world");
+    if (rank != h->rank || world != h->world) h->plan_dirty = true;
+    h->rank = rank;
+    h->world = world;
+    return JME_OK;
+}
+
+int jme_set_stream(jme_handle_t* h, void* stream) {
+    if (!h) return JME_ERR_INVALID;
+    h->stream = stream ? static_cast<cudaStream_t>(stream) : h->own_stream;
+    return JME_OK;
+}
+
+static int coords_from_device_aos(jme_handle* h, const double* d_xyz) {
+    const int n = h->ds.n;
+    if (n > 0) {
+        aos_to_soa_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(d_xyz, n, h->d_x, h->d_y, h->d_z);
+        ++h->launches;
+        JME_CUDA(h, cudaGetLastError());
+    }
+    h->coords_set = true;
+    h->cells.coords_changed();
+    return JME_OK;
+}
+
+int jme_set_coords(jme_handle_t* h, const double* xyz, int64_t n_atoms) {
+    if (!h) return JME_ERR_INVALID;
+    if (n_atoms != h->hs.n) return fail(h, JME_ERR_INVALID, "atom count differs from the parameterised system");
+    if (n_atoms > 0 && !xyz) return fail(h, JME_ERR_INVALID, "null coordinates");
+    JME_CUDA(h, cudaSetDevice(h->device));
+    if (n_atoms > 0)
+        JME_CUDA(h, cudaMemcpyAsync(h->d_xyz_stage, xyz, 3 * (size_t)n_atoms * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    return coords_from_device_aos(h, h->d_xyz_stage);
+}
+
+int jme_set_coords_device(jme_handle_t* h, const double* d_xyz, int64_t n_atoms) {
+    if (!h) return JME_ERR_INVALID;
+    if (n_atoms != h->hs.n) return fail(h, JME_ERR_INVALID, "atom count differs from the parameterised system");
+    if (n_atoms > 0 && !d_xyz) return fail(h, JME_ERR_INVALID, "null coordinates");
+    return coords_from_device_aos(h, d_xyz);
+}
+
+int jme_set_coord1(jme_handle_t* h, int64_t atom, int axis, double value) {
+    if (!h) return JME_ERR_INVALID;
+    if (atom < 0 || atom >= h->hs.n || axis < 0 || axis > 2) return fail(h, JME_ERR_INVALID, "atom or axis out of range");
+    if (!h->coords_set) return fail(h, JME_ERR_NOT_ASSIGNED, "set all coordinates once before moving single ones");
+    set_coord1_kernel<<<1, 1, 0, h->stream>>>(h->d_x, h->d_y, h->d_z, (int)atom, axis, value);
+    ++h->launches;
+    JME_CUDA(h, cudaGetLastError());
+    h->cells.coords_changed();
+    return JME_OK;
+}
+
+int jme_get_coords(jme_handle_t* h, double* xyz, int64_t n_atoms) {
+    if (!h || !xyz) return JME_ERR_INVALID;
+    if (n_atoms != h->hs.n) return fail(h, JME_ERR_INVALID, "atom count differs");
+    if (!h->coords_set) return fail(h, JME_ERR_NOT_ASSIGNED, "no coordinates set");
+    const int n = h->ds.n;
+    if (n == 0) return JME_OK;
+    soa_to_aos_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_x, h->d_y, h->d_z, n, h->d_xyz_stage);
+    ++h->launches;
+    JME_CUDA(h, cudaGetLastError());
+    JME_CUDA(h, cudaMemcpyAsync(xyz, h->d_xyz_stage, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    JME_CUDA(h, cudaStreamSynchronize(h->stream));
+    return JME_OK;
+}
+
+int jme_energy(jme_handle_t* h, double* total, double comps[JME_N_COMPONENTS]) {
+    if (!h) return JME_ERR_INVALID;
+    JME_CUDA(h, cudaSetDevice(h->device));
+    int rc = enqueue_eval(h, false, nullptr);
+    if (rc) return rc;
+    return finish_host(h, false, total, comps, nullptr);
+}
+
+int jme_energy_gradient(jme_handle_t* h, double* total, double comps[JME_N_COMPONENTS], double* grad_xyz) {
+    if (!h) return JME_ERR_INVALID;
+    if (!grad_xyz && h->hs.n > 0) return fail(h, JME_ERR_INVALID, "null gradient buffer");
+    JME_CUDA(h, cudaSetDevice(h->device));
+    int rc = enqueue_eval(h, true, nullptr);
+    if (rc) return rc;
+    return finish_host(h, true, total, comps, grad_xyz);
+}
+
+int64_t jme_eval_out_size(const jme_handle_t* h, int want_gradient) {
+    if (!h) return 0;
+    return kOutHeader + (want_gradient ? 3 * h->hs.n : 0);
+}
+
+int jme_eval_device(jme_handle_t* h, int want_gradient, double* d_out) {
+    if (!h || !d_out) return JME_ERR_INVALID;
+    return enqueue_eval(h, want_gradient != 0, d_out);
+}
+
+int jme_pair_stats(jme_handle_t* h, uint64_t* pairs_evaluated, uint64_t* pairs_candidate) {
+    if (!h) return JME_ERR_INVALID;
+    if (pairs_evaluated) *pairs_evaluated = h->last_pairs;
+    if (pairs_candidate) *pairs_candidate = h->last_cand;
+    return JME_OK;
+}
+
+int jme_pair_list(jme_handle_t* h, int32_t* pair_i, int32_t* pair_j, uint8_t* is14, int64_t capacity, int64_t* n_pairs) {
+    if (!h || !n_pairs || capacity < 0) return JME_ERR_INVALID;
+    if (!h->coords_set) return fail(h, JME_ERR_NOT_ASSIGNED, "no coordinates set");
+    JME_CUDA(h, cudaSetDevice(h->device));
+    int rc;
+    if ((rc = ensure_plan(h))) return rc;
+    int *d_i = nullptr, *d_j = nullptr;
+    unsigned char* d_f = nullptr;
+    unsigned long long* d_cur = nullptr;
+    const size_t cap = (size_t)std::max<int64_t>(1, capacity);
+    JME_CUDA(h, cudaMalloc(&d_i, cap * sizeof(int)));
+    JME_CUDA(h, cudaMalloc(&d_j, cap * sizeof(int)));
+    JME_CUDA(h, cudaMalloc(&d_f, cap));
+    JME_CUDA(h, cudaMalloc(&d_cur, sizeof(unsigned long long)));
+    JME_CUDA(h, cudaMemsetAsync(d_cur, 0, sizeof(unsigned long long), h->stream));
+    rc = JME_OK;
+    if (h->active_path == JME_PATH_ALLPAIRS) {
+        const int n_items = h->item_end - h->item_begin;
+        if (n_items > 0) {
+            const int grid = (n_items + kApWarps - 1) / kApWarps;
+            if (h->cutoff > 0)
+                ap_pairlist_kernel<true><<<grid, kApThreads, 0, h->stream>>>(h->ds, h->d_items, h->item_begin, h->item_end, h->d_tile_mask, h->d_masks, d_i, d_j, d_f, capacity, d_cur);
+            else
+                ap_pairlist_kernel<false><<<grid, kApThreads, 0, h->stream>>>(h->ds, h->d_items, h->item_begin, h->item_end, h->d_tile_mask, h->d_masks, d_i, d_j, d_f, capacity, d_cur);
+            ++h->launches;
+        }
+    } else {
+        rc = run_cell_pairlist(h->cells, h->ds, d_i, d_j, d_f, capacity, d_cur, h->stream, h->launches, h->err);
+    }
+    unsigned long long cnt = 0;
+    cudaError_t ce = cudaMemcpyAsync(&cnt, d_cur, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+    const size_t m = (size_t)std::min<unsigned long long>(cnt, (unsigned long long)capacity);
+    if (ce == cudaSuccess && m > 0 && pair_i && pair_j && is14) {
+        cudaMemcpy(pair_i, d_i, m * sizeof(int), cudaMemcpyDeviceToHost);
+        cudaMemcpy(pair_j, d_j, m * sizeof(int), cudaMemcpyDeviceToHost);
+        ce = cudaMemcpy(is14, d_f, m, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_i); cudaFree(d_j); cudaFree(d_f); cudaFree(d_cur);
+    if (ce != cudaSuccess) return fail(h, JME_ERR_CUDA, std::string("pair list: ") + cudaGetErrorString(ce));
+    *n_pairs = (int64_t)cnt;
+    return rc;
+}
+
+int jme_measure_fp64_peak(double* tflops, double* sm_clock_mhz_estimate) {
+    if (!tflops) return JME_ERR_INVALID;
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return JME_ERR_CUDA;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+    double* d = nullptr;
+    if (cudaMalloc(&d, (size_t)blocks * threads * sizeof(double)) != cudaSuccess) return JME_ERR_CUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e0);
+        dfma_peak_kernel<<<blocks, threads>>>(d, iters, 1.0000001, 1e-9);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return JME_ERR_CUDA; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    const double fma_count = (double)blocks * threads * (double)iters * 8.0;
+    *tflops = 2.0 * fma_count / (best * 1e-3) / 1e12;
+    if (sm_clock_mhz_estimate)   // 64 FP64 FMA lanes per SM per clock on sm_100
+        *sm_clock_mhz_estimate = fma_count / (best * 1e-3) / (64.0 * prop.multiProcessorCount) / 1e6;
+    return JME_OK;
+}
+
+int jme_enumerate_terms(int64_t n_atoms, const int32_t* atom_type, const uint8_t* linear, int64_t n_bonds,
+                        const int32_t* bond_i, const int32_t* bond_j, int32_t* angles, int64_t* n_angles,
+                        int32_t* oops, int64_t* n_oops, int32_t* torsions, int64_t* n_torsions) {
+    if (n_atoms < 0 || n_bonds < 0 || !n_angles || !n_oops || !n_torsions) return JME_ERR_INVALID;
+    if (n_atoms > 0 && (!atom_type || !linear)) return JME_ERR_INVALID;
+    if (n_bonds > 0 && (!bond_i || !bond_j)) return JME_ERR_INVALID;
+    for (int64_t b = 0; b < n_bonds; ++b)
+        if (bond_i[b] < 0 || bond_i[b] >= n_atoms || bond_j[b] < 0 || bond_j[b] >= n_atoms) return JME_ERR_INVALID;
+    std::vector<int32_t> A, O, T;
+    enumerate_terms(n_atoms, atom_type, linear, n_bonds, bond_i, bond_j, A, O, T);
+    if (angles) std::copy(A.begin(), A.end(), angles);
+    if (oops) std::copy(O.begin(), O.end(), oops);
+    if (torsions) std::copy(T.begin(), T.end(), torsions);
+    *n_angles = (int64_t)A.size() / 3;
+    *n_oops = (int64_t)O.size() / 4;
+    *n_torsions = (int64_t)T.size() / 4;
+    return JME_OK;
+}
+
+int jme_exclusions(int64_t n_atoms, int64_t n_bonds, const int32_t* bond_i, const int32_t* bond_j,
+                   int64_t* row_ptr, int32_t* partner, uint8_t* is14, int64_t capacity, int64_t* n_entries) {
+    if (n_atoms < 0 || n_bonds < 0 || !n_entries) return JME_ERR_INVALID;
+    for (int64_t b = 0; b < n_bonds; ++b)
+        if (bond_i[b] < 0 || bond_i[b] >= n_atoms || bond_j[b] < 0 || bond_j[b] >= n_atoms) return JME_ERR_INVALID;
+    std::vector<int64_t> ptr;
+    std::vector<uint32_t> ent;
+    build_exclusions(n_atoms, n_bonds, bond_i, bond_j, ptr, ent);
+    *n_entries = (int64_t)ent.size();
+    if (row_ptr) std::copy(ptr.begin(), ptr.end(), row_ptr);
+    if (partner && is14)
+        for (int64_t e = 0; e < std::min<int64_t>(capacity, (int64_t)ent.size()); ++e) {
+            partner[e] = (int32_t)(ent[e] & ~kFlag14);
+            is14[e] = (ent[e] & kFlag14) ? 1 : 0;
+        }
+    return JME_OK;
+}
+
+}  // extern "C"

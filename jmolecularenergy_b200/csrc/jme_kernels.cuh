@@ -1,0 +1,490 @@
+// jme_kernels.cuh - CUDA kernels of the MMFF94 energy/gradient path for sm_100a (B200).
+//
+// Nothing here is a dense contraction, so tensor cores are deliberately unused: the nonbonded
+// kernels are bound by the FP64 FMA pipe (about 58 FP64 instructions per pair), everything else by
+// HBM/L2 bandwidth or launch latency.  Design notes per kernel are in DESIGN.md.
+//
+//   ap_kernel        all-pairs tiles: one warp = one 32-atom i-block x a run of 32-atom j-tiles,
+//                    j-tile staged in shared memory, Newton's third law inside every tile with the
+//                    j-accumulators rotating through the warp, exclusions / 1-4 flags as 32x32 bit
+//                    masks, deterministic (every partial gradient has exactly one writer).
+//   bonded_kernel    one thread per bonded term, gradients to per-term slots.
+//   reduce_kernel    per-atom fixed-order sum of the tile partials and bonded slots (CSR gather),
+//                    unit conversion, energy/pair-count tree reduction.
+//   cells_*          cell-list path for cutoff > 0 (jme_cells.cuh).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "jme_math.cuh"
+
+namespace jme {
+
+constexpr int kTile = 32;
+constexpr int kApWarps = 4;                    // warps per CTA in ap_kernel
+constexpr int kApThreads = kApWarps * 32;
+constexpr int kReduceWarps = 8;
+constexpr int kBondedThreads = 128;
+
+struct DeviceSystem {
+    int n;                 // atoms
+    int n_pad;             // padded to a multiple of 32
+    int n_blocks;          // n_pad / 32
+    int n_types;
+    const double* x;       // [n_pad] SoA coordinates (padding = 0)
+    const double* y;
+    const double* z;
+    const double* q;       // [n_pad] charges (padding = 0)
+    const int* type;       // [n_pad] dense type index (padding = 0)
+    const PairConst* table;    // [n_types*n_types]
+    double r2_max;         // cutoff threshold on r^2 (jme_host.hpp cutoff_r2_threshold); unused without cutoff
+    double ele_scale;      // 332.0716 / dielectric
+};
+
+// One work item of the all-pairs path: i-block I against j-blocks J = (I + d) mod n_blocks for
+// d in [d0, d0 + nd).  d = 0 is the diagonal tile.  tile_ofs indexes tile_mask[].
+struct ApItem {
+    int I, d0, nd, tile_ofs;
+};
+
+struct TileMask {
+    uint32_t excl[32];     // row = i-lane, bit = j index in the tile: pair excluded (1-2, 1-3, padding)
+    uint32_t f14[32];      // pair is a 1-4 pair (electrostatics x0.75)
+};
+
+__device__ __forceinline__ double shfl_rot1(double v, int src_lane) {
+    return __shfl_sync(0xffffffffu, v, src_lane);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// all-pairs tiles
+// ---------------------------------------------------------------------------------------------
+// gpart layout: [slot][3][n_pad].  Slot I (< n_blocks) receives the j-side gradients produced by the
+// items of i-block I; slot n_blocks + c receives the i-side gradients of chunk c of every row.  Each
+// (slot, atom) has exactly one writer, so the later fixed-order sum is deterministic.
+template <bool GRAD, bool CUTOFF>
+__global__ void __launch_bounds__(kApThreads, 4)
+ap_kernel(DeviceSystem S, const ApItem* __restrict__ items, int item_begin, int item_end,
+          const int* __restrict__ tile_mask, const TileMask* __restrict__ masks,
+          double* __restrict__ gpart, int chunk_slot_base, int tiles_per_item,
+          double* __restrict__ epart, unsigned long long* __restrict__ cpart) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // shared: pair table, then per-warp j staging (x, y, z, q: 4 x 32 doubles; type: 32 ints)
+    PairConst* s_table = reinterpret_cast<PairConst*>(smem_raw);
+    const int TT = S.n_types * S.n_types;
+    double* s_stage = reinterpret_cast<double*>(s_table + TT);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* sx = s_stage + warp * (4 * 32 + 16);
+    double* sy = sx + 32;
+    double* sz = sy + 32;
+    double* sq = sz + 32;
+    int* st = reinterpret_cast<int*>(sq + 32);
+
+    for (int t = threadIdx.x; t < TT; t += kApThreads) s_table[t] = S.table[t];
+    __syncthreads();
+
+    const int item_idx = item_begin + blockIdx.x * kApWarps + warp;
+    if (item_idx >= item_end) return;
+    const ApItem it = items[item_idx];
+
+    const int ia = it.I * kTile + lane;
+    const double xi = S.x[ia], yi = S.y[ia], zi = S.z[ia];
+    const double qi = S.ele_scale * S.q[ia];
+    const PairConst* trow = s_table + S.type[ia] * S.n_types;
+
+    double gix = 0, giy = 0, giz = 0, ev = 0, ee = 0;
+    unsigned int n_eval = 0, n_cand = 0;
+
+    // software pipeline: the next tile's atoms are loaded into registers while this tile computes
+    int Jn = it.I + it.d0;
+    if (Jn >= S.n_blocks) Jn -= S.n_blocks;
+    double px = S.x[Jn * kTile + lane], py = S.y[Jn * kTile + lane], pz = S.z[Jn * kTile + lane];
+    double pq = S.q[Jn * kTile + lane];
+    int pt = S.type[Jn * kTile + lane];
+    int pm = tile_mask[it.tile_ofs];
+
+    for (int t = 0; t < it.nd; ++t) {
+        const int d = it.d0 + t;
+        const int J = Jn;
+        __syncwarp();
+        sx[lane] = px;
+        sy[lane] = py;
+        sz[lane] = pz;
+        sq[lane] = pq;
+        st[lane] = pt;
+        uint32_t m_excl = 0, m_14 = 0;
+        if (pm >= 0) {
+            m_excl = masks[pm].excl[lane];
+            m_14 = masks[pm].f14[lane];
+        }
+        __syncwarp();
+        if (t + 1 < it.nd) {
+            Jn = it.I + d + 1;
+            if (Jn >= S.n_blocks) Jn -= S.n_blocks;
+            const int na = Jn * kTile + lane;
+            px = S.x[na]; py = S.y[na]; pz = S.z[na]; pq = S.q[na]; pt = S.type[na];
+            pm = tile_mask[it.tile_ofs + t + 1];
+        }
+
+        const bool diag = (d == 0);
+        const int k_begin = diag ? 1 : 0;
+        const int k_end = diag ? 17 : 32;      // diagonal: offsets 1..16, offset 16 only from lanes < 16
+        double gjx = 0, gjy = 0, gjz = 0;
+        for (int k = k_begin; k < k_end; ++k) {
+            if (GRAD && k != k_begin) {
+                const int src = (lane + 1) & 31;
+                gjx = shfl_rot1(gjx, src);
+                gjy = shfl_rot1(gjy, src);
+                gjz = shfl_rot1(gjz, src);
+            }
+            const int jj = (lane + k) & 31;
+            const double dx = xi - sx[jj], dy = yi - sy[jj], dz = zi - sz[jj];
+            double r2;
+            if (CUTOFF) {
+                // strict double, left-to-right, no FMA: the r2 the reference's Point3d.distance squares
+                r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            } else {
+                r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            }
+            bool on = !((m_excl >> jj) & 1u);
+            if (diag && k == 16) on = on && (lane < 16);
+            n_cand += __popc(__ballot_sync(0xffffffffu, on));
+            if (CUTOFF) {
+                on = on && !(r2 > S.r2_max);
+                n_eval += __popc(__ballot_sync(0xffffffffu, on));
+            }
+            double qq = qi * sq[jj];
+            if ((m_14 >> jj) & 1u) qq *= kEle14;
+            double e1, e2, f;
+            // coincident atoms (r2 == 0, tested on the exponent bits): the buffered energies are finite
+            // there and are kept; the gradient direction is undefined and f * dx = 0 contributes nothing
+            const bool tiny = __double2hiint(r2) < 0x00100000;
+            pair_terms<GRAD>((on && !tiny) ? r2 : (on ? 1e-300 : 1.0), trow[st[jj]], qq, e1, e2, f);
+            e1 = on ? e1 : 0.0;
+            e2 = on ? e2 : 0.0;
+            ev += e1;
+            ee += e2;
+            if (GRAD) {
+                f = on ? f : 0.0;
+                gix = fma(f, dx, gix);
+                giy = fma(f, dy, giy);
+                giz = fma(f, dz, giz);
+                gjx = fma(-f, dx, gjx);
+                gjy = fma(-f, dy, gjy);
+                gjz = fma(-f, dz, gjz);
+            }
+        }
+        if (GRAD) {
+            // after the last step the accumulator in lane l belongs to tile atom (l + k_end - 1) & 31
+            const int jo = J * kTile + ((lane + k_end - 1) & 31);
+            double* gj = gpart + (size_t)it.I * 3 * S.n_pad;
+            gj[jo] = gjx;
+            gj[S.n_pad + jo] = gjy;
+            gj[2 * S.n_pad + jo] = gjz;
+        }
+    }
+    if (GRAD) {
+        const int chunk = it.d0 / tiles_per_item;
+        double* gi = gpart + (size_t)(chunk_slot_base + chunk) * 3 * S.n_pad;
+        gi[ia] = gix;
+        gi[S.n_pad + ia] = giy;
+        gi[2 * S.n_pad + ia] = giz;
+    }
+    ev = warp_sum(ev);
+    ee = warp_sum(ee);
+    if (lane == 0) {
+        epart[2 * item_idx] = ev;
+        epart[2 * item_idx + 1] = ee;
+        // ballots are warp-uniform: every lane holds the same counts
+        cpart[2 * item_idx] = CUTOFF ? n_eval : n_cand;
+        cpart[2 * item_idx + 1] = n_cand;
+    }
+}
+
+// Diagnostic twin of ap_kernel: same traversal and predicate, emits the selected pairs instead of
+// evaluating them (jme_pair_list).  Order is arbitrary; callers sort.
+template <bool CUTOFF>
+__global__ void __launch_bounds__(kApThreads)
+ap_pairlist_kernel(DeviceSystem S, const ApItem* __restrict__ items, int item_begin, int item_end,
+                   const int* __restrict__ tile_mask, const TileMask* __restrict__ masks,
+                   int* __restrict__ out_i, int* __restrict__ out_j, unsigned char* __restrict__ out_14,
+                   long long capacity, unsigned long long* __restrict__ cursor) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item_idx = item_begin + blockIdx.x * kApWarps + warp;
+    if (item_idx >= item_end) return;
+    const ApItem it = items[item_idx];
+    const int ia = it.I * kTile + lane;
+    const double xi = S.x[ia], yi = S.y[ia], zi = S.z[ia];
+    for (int t = 0; t < it.nd; ++t) {
+        const int d = it.d0 + t;
+        int J = it.I + d;
+        if (J >= S.n_blocks) J -= S.n_blocks;
+        uint32_t m_excl = 0, m_14 = 0;
+        const int mi = tile_mask[it.tile_ofs + t];
+        if (mi >= 0) {
+            m_excl = masks[mi].excl[lane];
+            m_14 = masks[mi].f14[lane];
+        }
+        const bool diag = (d == 0);
+        const int k_begin = diag ? 1 : 0, k_end = diag ? 17 : 32;
+        for (int k = k_begin; k < k_end; ++k) {
+            const int jj = (lane + k) & 31;
+            const int ja = J * kTile + jj;
+            const double dx = xi - S.x[ja], dy = yi - S.y[ja], dz = zi - S.z[ja];
+            const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            bool on = !((m_excl >> jj) & 1u);
+            if (diag && k == 16) on = on && (lane < 16);
+            if (CUTOFF) on = on && !(r2 > S.r2_max);
+            if (on) {
+                const unsigned long long p = atomicAdd(cursor, 1ull);
+                if ((long long)p < capacity) {
+                    out_i[p] = min(ia, ja);
+                    out_j[p] = max(ia, ja);
+                    out_14[p] = (m_14 >> jj) & 1u;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bonded terms: one thread per term
+// ---------------------------------------------------------------------------------------------
+struct BondedTerms {
+    int n_bond, n_angle, n_oop, n_tor;
+    const int* bond_at;       // [n_bond][2]
+    const double* bond_par;   // [n_bond][2]
+    const int* angle_at;      // [n_angle][3]
+    const double* angle_par;  // [n_angle][6]
+    const unsigned char* angle_linear;
+    const int* oop_at;        // [n_oop][4]
+    const double* oop_par;    // [n_oop]
+    const int* tor_at;        // [n_tor][4]
+    const double* tor_par;    // [n_tor][3]
+};
+
+__device__ __forceinline__ Vec3 load_pos(const DeviceSystem& S, int a) { return Vec3{S.x[a], S.y[a], S.z[a]}; }
+__device__ __forceinline__ void store_slot(double* slots, long long s, Vec3 g) {
+    slots[3 * s] = g.x;
+    slots[3 * s + 1] = g.y;
+    slots[3 * s + 2] = g.z;
+}
+
+// Terms [term_begin, term_end) of the concatenated list bonds | angles | oops | torsions.
+// Slot numbering: bond b -> 2b, 2b+1; angle a -> 2nb + 3a + {0,1,2}; oop o -> 2nb + 3na + 4o + {0..3};
+// torsion t -> 2nb + 3na + 4no + 4t + {0..3}.  bpart: [gridDim.x][5] block partial energies.
+template <bool GRAD>
+__global__ void __launch_bounds__(kBondedThreads)
+bonded_kernel(DeviceSystem S, BondedTerms B, long long term_begin, long long term_end,
+              double* __restrict__ slots, double* __restrict__ bpart) {
+    const long long t = term_begin + (long long)blockIdx.x * kBondedThreads + threadIdx.x;
+    double e[5] = {0, 0, 0, 0, 0};
+    if (t < term_end) {
+        long long u = t;
+        if (u < B.n_bond) {
+            const int i = B.bond_at[2 * u], j = B.bond_at[2 * u + 1];
+            Vec3 gi, gj;
+            e[0] = bond_term(load_pos(S, i), load_pos(S, j), B.bond_par[2 * u], B.bond_par[2 * u + 1], gi, gj);
+            if (GRAD) { store_slot(slots, 2 * u, gi); store_slot(slots, 2 * u + 1, gj); }
+        } else if ((u -= B.n_bond) < B.n_angle) {
+            const int i = B.angle_at[3 * u], j = B.angle_at[3 * u + 1], k = B.angle_at[3 * u + 2];
+            const double* p = B.angle_par + 6 * u;
+            Vec3 gi, gj, gk;
+            angle_stbn_term(load_pos(S, i), load_pos(S, j), load_pos(S, k), p[0], p[1], B.angle_linear[u] != 0,
+                            p[2], p[3], p[4], p[5], e[1], e[2], gi, gj, gk);
+            if (GRAD) {
+                const long long s = 2ll * B.n_bond + 3 * u;
+                store_slot(slots, s, gi); store_slot(slots, s + 1, gj); store_slot(slots, s + 2, gk);
+            }
+        } else if ((u -= B.n_angle) < B.n_oop) {
+            const int* at = B.oop_at + 4 * u;
+            Vec3 gi, gj, gk, gl;
+            e[3] = oop_term(load_pos(S, at[0]), load_pos(S, at[1]), load_pos(S, at[2]), load_pos(S, at[3]), B.oop_par[u], gi, gj, gk, gl);
+            if (GRAD) {
+                const long long s = 2ll * B.n_bond + 3ll * B.n_angle + 4 * u;
+                store_slot(slots, s, gi); store_slot(slots, s + 1, gj); store_slot(slots, s + 2, gk); store_slot(slots, s + 3, gl);
+            }
+        } else {
+            u -= B.n_oop;
+            const int* at = B.tor_at + 4 * u;
+            const double* p = B.tor_par + 3 * u;
+            Vec3 gi, gj, gk, gl;
+            e[4] = torsion_term(load_pos(S, at[0]), load_pos(S, at[1]), load_pos(S, at[2]), load_pos(S, at[3]), p[0], p[1], p[2], gi, gj, gk, gl);
+            if (GRAD) {
+                const long long s = 2ll * B.n_bond + 3ll * B.n_angle + 4ll * B.n_oop + 4 * u;
+                store_slot(slots, s, gi); store_slot(slots, s + 1, gj); store_slot(slots, s + 2, gk); store_slot(slots, s + 3, gl);
+            }
+        }
+    }
+    __shared__ double s_e[kBondedThreads / 32][5];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        const double v = warp_sum(e[c]);
+        if (lane == 0) s_e[warp][c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double v = 0;
+        for (int w = 0; w < kBondedThreads / 32; ++w) v += s_e[w][threadIdx.x];
+        bpart[5 * blockIdx.x + threadIdx.x] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// final reduction
+// ---------------------------------------------------------------------------------------------
+struct ReduceArgs {
+    int n, n_pad;
+    const double* gpart;            // [n_slots][3][n_pad]
+    int n_slots;
+    const double* direct;           // optional [3][n_pad] gradient written directly per atom (cell path), or null
+    const double* slots;            // bonded slots
+    const long long* slot_ptr;      // [n+1] CSR atom -> bonded slot ids (ascending)
+    const long long* slot_idx;
+    long long slot_lo, slot_hi;     // only slots in [slot_lo, slot_hi) were written by this shard
+    const double* epart; int n_epart;               // [n_epart][2] (vdw, ele)
+    const unsigned long long* cpart;                // [n_epart][2] (evaluated, candidates)
+    const double* bpart; int n_bpart;               // [n_bpart][5]
+    double unit_num, unit_den;      // (v * num) / den, ForceField.java:157; both 1 for kcal/mol
+    int want_grad;
+    double* out;                    // [0] total [1..7] comps [8] pairs evaluated [9] candidates [10..] gradient AoS
+};
+constexpr int kOutHeader = 10;
+
+__device__ __forceinline__ double convert_unit(double v, double num, double den) {
+    return (num == den) ? v : (v * num) / den;
+}
+
+__global__ void __launch_bounds__(kReduceWarps * 32)
+reduce_kernel(ReduceArgs A) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_atom_blocks = (A.n + 31) / 32;
+    __shared__ double s_g[kReduceWarps][3][32];
+    // energy-only launches have a single block: the energy block
+    const int bid = blockIdx.x + (A.want_grad ? 0 : n_atom_blocks);
+    if (bid < n_atom_blocks) {
+        const int a = bid * 32 + lane;
+        double gx = 0, gy = 0, gz = 0;
+        for (int s = warp; s < A.n_slots; s += kReduceWarps) {
+            const double* p = A.gpart + (size_t)s * 3 * A.n_pad + a;
+            gx += p[0];
+            gy += p[A.n_pad];
+            gz += p[2 * (size_t)A.n_pad];
+        }
+        s_g[warp][0][lane] = gx;
+        s_g[warp][1][lane] = gy;
+        s_g[warp][2][lane] = gz;
+        __syncthreads();
+        if (warp == 0 && a < A.n) {
+            gx = gy = gz = 0;
+#pragma unroll
+            for (int w = 0; w < kReduceWarps; ++w) {
+                gx += s_g[w][0][lane];
+                gy += s_g[w][1][lane];
+                gz += s_g[w][2][lane];
+            }
+            if (A.direct) {
+                gx += A.direct[a];
+                gy += A.direct[A.n_pad + a];
+                gz += A.direct[2 * (size_t)A.n_pad + a];
+            }
+            for (long long e = A.slot_ptr[a]; e < A.slot_ptr[a + 1]; ++e) {
+                const long long s = A.slot_idx[e];
+                if (s >= A.slot_lo && s < A.slot_hi) {
+                    gx += A.slots[3 * s];
+                    gy += A.slots[3 * s + 1];
+                    gz += A.slots[3 * s + 2];
+                }
+            }
+            double* o = A.out + kOutHeader + 3 * (size_t)a;
+            o[0] = convert_unit(gx, A.unit_num, A.unit_den);
+            o[1] = convert_unit(gy, A.unit_num, A.unit_den);
+            o[2] = convert_unit(gz, A.unit_num, A.unit_den);
+        }
+        return;
+    }
+    // last block: energies and pair counts, fixed-order strided sums + shared-memory tree
+    constexpr int NT = kReduceWarps * 32;
+    __shared__ double s_e[7][NT];
+    __shared__ unsigned long long s_c[2][NT];
+    double e[7] = {0, 0, 0, 0, 0, 0, 0};
+    unsigned long long c0 = 0, c1 = 0;
+    for (int i = threadIdx.x; i < A.n_bpart; i += NT)
+        for (int c = 0; c < 5; ++c) e[c] += A.bpart[5 * (size_t)i + c];
+    for (int i = threadIdx.x; i < A.n_epart; i += NT) {
+        e[5] += A.epart[2 * (size_t)i];
+        e[6] += A.epart[2 * (size_t)i + 1];
+        c0 += A.cpart[2 * (size_t)i];
+        c1 += A.cpart[2 * (size_t)i + 1];
+    }
+    for (int c = 0; c < 7; ++c) s_e[c][threadIdx.x] = e[c];
+    s_c[0][threadIdx.x] = c0;
+    s_c[1][threadIdx.x] = c1;
+    __syncthreads();
+    for (int o = NT / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            for (int c = 0; c < 7; ++c) s_e[c][threadIdx.x] += s_e[c][threadIdx.x + o];
+            s_c[0][threadIdx.x] += s_c[0][threadIdx.x + o];
+            s_c[1][threadIdx.x] += s_c[1][threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double total = 0;
+        for (int c = 0; c < 7; ++c) {      // MMFF94.java:390-392: sum in component order
+            const double v = convert_unit(s_e[c][0], A.unit_num, A.unit_den);
+            A.out[1 + c] = v;
+            total += v;
+        }
+        A.out[0] = total;
+        A.out[8] = (double)s_c[0][0];
+        A.out[9] = (double)s_c[1][0];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// marshalling helpers
+// ---------------------------------------------------------------------------------------------
+__global__ void aos_to_soa_kernel(const double* __restrict__ xyz, int n, double* __restrict__ x,
+                                  double* __restrict__ y, double* __restrict__ z) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < n) {
+        x[a] = xyz[3 * (size_t)a];
+        y[a] = xyz[3 * (size_t)a + 1];
+        z[a] = xyz[3 * (size_t)a + 2];
+    }
+}
+
+__global__ void soa_to_aos_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                  const double* __restrict__ z, int n, double* __restrict__ xyz) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < n) {
+        xyz[3 * (size_t)a] = x[a];
+        xyz[3 * (size_t)a + 1] = y[a];
+        xyz[3 * (size_t)a + 2] = z[a];
+    }
+}
+
+__global__ void set_coord1_kernel(double* x, double* y, double* z, int atom, int axis, double value) {
+    (axis == 0 ? x : axis == 1 ? y : z)[atom] = value;
+}
+
+// FP64 FMA-pipe peak: 8 independent dependent-chains of DFMA per thread.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
+    double v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        v0 = fma(v0, a, b); v1 = fma(v1, a, b); v2 = fma(v2, a, b); v3 = fma(v3, a, b);
+        v4 = fma(v4, a, b); v5 = fma(v5, a, b); v6 = fma(v6, a, b); v7 = fma(v7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+}
+
+}  // namespace jme

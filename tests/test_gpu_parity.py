@@ -1,0 +1,304 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes -> libjme_b200.so), against
+the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): total energy <= 1e-10 relative, per-atom gradient component
+<= 1e-8 relative with an absolute floor of 1e-10 x the largest component; pair selection bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+PINNED = golden_names()
+ALL = golden_names(pinned_only=False)
+E_RTOL = 1e-10
+G_RTOL = 1e-8
+
+
+def gpu_ff(path="auto", cutoff=0.0, dielectric=1.0, unit=None):
+    from jmolecularenergy_b200 import MMFF94, EnergyUnit
+    ff = MMFF94(False, path=path)
+    ff.setCutoffDistance(cutoff)
+    ff.setDielectricConstant(dielectric)
+    if unit is not None:
+        ff.setEnergyUnit(EnergyUnit[unit])
+    return ff
+
+
+def assert_parity(got, ref, label=""):
+    for k in ("bond", "angle", "stretch_bend", "oop", "torsion", "vdw", "ele"):
+        scale = max(abs(ref[k]), abs(ref["total"]), 1e-3)
+        assert abs(got[k] - ref[k]) <= E_RTOL * scale, (label, k, got[k], ref[k])
+    assert abs(got["total"] - ref["total"]) <= E_RTOL * max(abs(ref["total"]), 1e-3), (label, got["total"], ref["total"])
+    assert got["pairs"] == ref["pairs"], (label, got["pairs"], ref["pairs"])
+    if "gradient" in ref:
+        g = ref["gradient"]
+        floor = 1e-10 * max(1.0, float(np.abs(g).max()))
+        np.testing.assert_allclose(got["gradient"], g, rtol=G_RTOL, atol=floor, err_msg=label)
+
+
+@pytest.mark.parametrize("name", PINNED)
+def test_golden_energy_matches_published_value(name):
+    """The reference's own criterion (MMFF94Test.java:79-81) through the GPU path, at 1e-5 not 1e-2."""
+    s = load_golden(name)
+    ff = gpu_ff()
+    ff.assignParameters(s)
+    assert abs(ff.calculateEnergy(s) - s.expected_energy) <= 1e-5
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_golden_molecules_against_oracle(oracle, name):
+    s = load_golden(name)
+    ff = gpu_ff()
+    ff.assignParameters(s)
+    rng = np.random.default_rng(11)
+    for trial in range(3):
+        if trial:
+            s.xyz[:] = s.xyz + rng.normal(0, 0.08, size=s.xyz.shape)
+        assert_parity(ff.calculateComponents(s, gradient=True), oracle.evaluate(s, gradient=True), f"{name}#{trial}")
+
+
+def test_linear_centre_form(oracle):
+    s = load_golden("KHDFRM11")
+    s.linear[2] = 1
+    s.xyz[:] = s.xyz + np.random.default_rng(3).normal(0, 0.05, size=s.xyz.shape)
+    ff = gpu_ff()
+    ff.assignParameters(s)
+    assert_parity(ff.calculateComponents(s, gradient=True), oracle.evaluate(s, gradient=True))
+
+
+def test_chain_templates(oracle):
+    from jmolecularenergy_b200 import systems
+    rng = np.random.default_rng(5)
+    for name in ("DECANE", "DIGLYME_LIKE", "OCTANOL"):
+        s = systems.template(name)
+        s.xyz[:] = s.xyz + rng.normal(0, 0.05, size=s.xyz.shape)
+        ff = gpu_ff()
+        ff.assignParameters(s)
+        assert_parity(ff.calculateComponents(s, gradient=True), oracle.evaluate(s, gradient=True), name)
+
+
+@pytest.mark.parametrize("n_waters", [1, 10, 11, 100, 341])
+def test_water_boxes_all_pairs(oracle, n_waters):
+    """Block-count edge cases of the tile decomposition: 3, 30, 33 (one atom over a block), 300, 1023 atoms."""
+    from jmolecularenergy_b200 import systems
+    s = systems.water_box(n_waters)
+    ff = gpu_ff(path="allpairs")
+    ff.assignParameters(s)
+    assert_parity(ff.calculateComponents(s, gradient=True), oracle.evaluate(s, gradient=True), s.name)
+    e_only = ff.calculateEnergy(s)
+    assert e_only == pytest.approx(ff.calculateComponents(s, gradient=True)["total"], rel=1e-14)
+
+
+def test_config2_water_3k(oracle):
+    """BASELINE config 2: 1 000 waters, 4 495 500 pairs, full bonded + nonbonded energy/gradient."""
+    from jmolecularenergy_b200 import systems
+    s = systems.water_box(1000)
+    ff = gpu_ff()
+    ff.assignParameters(s)
+    got = ff.calculateComponents(s, gradient=True)
+    ref = oracle.evaluate(s, gradient=True)
+    assert ref["pairs"] == 4495500
+    assert_parity(got, ref, s.name)
+
+
+@pytest.mark.parametrize("path", ["allpairs", "cells"])
+@pytest.mark.parametrize("cutoff", [6.0, 9.5])
+def test_cutoff_paths_small(oracle, path, cutoff):
+    from jmolecularenergy_b200 import systems
+    s = systems.solvated_chains(2400, chain_fraction=0.3, exact_cutoff_pairs=12, cutoff=cutoff)
+    ff = gpu_ff(path=path, cutoff=cutoff)
+    ff.assignParameters(s)
+    ref = oracle.evaluate(s, cutoff=cutoff, gradient=True)
+    assert_parity(ff.calculateComponents(s, gradient=True), ref, f"{path}@{cutoff}")
+    # bit-exact pair selection, including the planted r == cutoff pairs
+    pi, pj, f14 = ff.pairList(s)
+    oi, oj, of = oracle.pair_list(s, cutoff=cutoff)
+    assert len(pi) == len(oi) == ref["pairs"]
+    assert np.array_equal(pi, oi) and np.array_equal(pj, oj) and np.array_equal(f14, of)
+    # one ulp below the cutoff the planted pairs drop out on both sides
+    c2 = float(np.nextafter(cutoff, 0))
+    ff.setCutoffDistance(c2)
+    n2 = len(ff.pairList(s)[0])
+    assert n2 == len(oracle.pair_list(s, cutoff=c2)[0])
+    assert len(pi) - n2 >= 12
+
+
+def test_pair_list_without_cutoff(oracle):
+    s = load_golden("ETHANOL")
+    ff = gpu_ff()
+    ff.assignParameters(s)
+    pi, pj, f14 = ff.pairList(s)
+    oi, oj, of = oracle.pair_list(s)
+    assert np.array_equal(pi, oi) and np.array_equal(pj, oj) and np.array_equal(f14, of)
+    assert len(pi) == 15 and int(f14.sum()) == 12
+
+
+@pytest.mark.parametrize("cutoff", [10.0, 12.0])
+def test_config3_solvated_25k(oracle, cutoff):
+    """BASELINE config 3: ~25 k atoms, cutoff 10 / 12 A, torsions + 1-4 scaling + exclusions + cell list,
+    >= 100 pairs planted at exactly r == cutoff.  Checker: the multi-threaded oracle (itself checked against
+    the reference-faithful evaluator in tests/test_oracle_fast.py)."""
+    from jmolecularenergy_b200 import systems
+    s = systems.solvated_chains(24999, exact_cutoff_pairs=100, cutoff=cutoff)
+    ff = gpu_ff(cutoff=cutoff)
+    ff.assignParameters(s)
+    got = ff.calculateComponents(s, gradient=True)
+    ref = oracle.fast_evaluate(s, cutoff=cutoff)
+    assert_parity(got, ref, s.name)
+    # the all-pairs tiles with the cutoff predicate must select the same pairs and agree to rounding
+    ff2 = gpu_ff(path="allpairs", cutoff=cutoff)
+    ff2.assignParameters(s)
+    got2 = ff2.calculateComponents(s, gradient=True)
+    assert got2["pairs"] == got["pairs"]
+    assert got2["total"] == pytest.approx(got["total"], rel=1e-12)
+    np.testing.assert_allclose(got2["gradient"], got["gradient"], rtol=1e-9, atol=1e-10 * np.abs(got["gradient"]).max())
+
+
+def test_config5_ion_box_125k(oracle):
+    from jmolecularenergy_b200 import systems
+    s = systems.ion_box(50)
+    ff = gpu_ff(cutoff=10.0)
+    ff.assignParameters(s)
+    got = ff.calculateComponents(s, gradient=True)
+    ref = oracle.fast_evaluate(s, cutoff=10.0)
+    assert_parity(got, ref, s.name)
+
+
+def test_config5_ion_box_1m_properties(oracle):
+    """BASELINE config 5 at full size (10^6 ions, cutoff 10 A): pair count and energy against the
+    multi-threaded oracle, plus size-independent properties - zero net force, run-to-run bit identity,
+    a 2-way shard sum equal to the unsharded result."""
+    from jmolecularenergy_b200 import systems
+    s = systems.ion_box(100)
+    ff = gpu_ff(cutoff=10.0)
+    ff.assignParameters(s)
+    a = ff.calculateComponents(s, gradient=True)
+    b = ff.calculateComponents(s, gradient=True)
+    assert a["total"] == b["total"] and np.array_equal(a["gradient"], b["gradient"])
+    net = np.abs(a["gradient"].sum(axis=0)).max()
+    assert net <= 1e-9 * np.abs(a["gradient"]).sum()
+    ref = oracle.fast_evaluate(s, cutoff=10.0, gradient=True)
+    assert_parity(a, ref, s.name)
+
+
+def test_units_and_dielectric(oracle):
+    from jmolecularenergy_b200 import systems
+    s = systems.water_box(40)
+    for unit in ("KJ_PER_MOL", "JOULE_PER_MOL"):
+        ff = gpu_ff(unit=unit, dielectric=2.5)
+        ff.assignParameters(s)
+        assert_parity(ff.calculateComponents(s, gradient=True),
+                      oracle.evaluate(s, unit=unit, dielectric=2.5, gradient=True), unit)
+
+
+def test_single_coordinate_update_equals_full_upload(oracle):
+    from jmolecularenergy_b200 import systems
+    s = systems.water_box(50)
+    ff = gpu_ff()
+    ff.assignParameters(s)
+    ff.calculateEnergy(s)
+    launches0 = ff.launchCount(s)
+    s.xyz[17, 1] += 0.013
+    e1 = ff.calculateEnergy(s)
+    # one set_coord1 + nonbonded + bonded + reduce
+    assert ff.launchCount(s) - launches0 == 4
+    t = systems.water_box(50)
+    t.xyz[:] = s.xyz
+    ff2 = gpu_ff()
+    ff2.assignParameters(t)
+    assert e1 == ff2.calculateEnergy(t)
+    assert e1 == pytest.approx(oracle.evaluate(s)["total"], rel=E_RTOL)
+
+
+def test_removed_component_is_not_summed(oracle):
+    s = load_golden("CO08A")
+    ff = gpu_ff()
+    ff.assignParameters(s)
+    full = ff.calculateComponents(s)
+    ff.removeEnergyComponent(ff.electrostaticComponent)
+    assert ff.calculateEnergy(s) == pytest.approx(full["total"] - full["ele"], rel=1e-12)
+    assert ff.vdwComponent.calculateEnergy(s) == pytest.approx(full["vdw"], rel=1e-14)
+
+
+def test_errors():
+    from jmolecularenergy_b200 import MMFF94, JmeError
+    from jmolecularenergy_b200 import systems
+    s = systems.water_box(3)
+    ff = MMFF94(False)
+    with pytest.raises(RuntimeError, match="MMFF94 parameters need to be assigned first"):
+        ff.calculateEnergy(s)
+    bad = systems.water_box(3)
+    bad.atom_type[0] = 12          # no vdW row for chlorine in a water system
+    with pytest.raises((JmeError, ValueError)):
+        ff.assignParameters(bad)
+    ff.assignParameters(s)
+    ff.setDielectricConstant(0.0)
+    with pytest.raises(JmeError):
+        ff.calculateEnergy(s)
+
+
+def test_two_way_shard_sums_to_unsharded(oracle):
+    """Atom-row sharding emulated on one GPU: two handles with rank 0/1 of 2; the
+    partial energies / gradients / pair counts must add up to the unsharded evaluation."""
+    from jmolecularenergy_b200 import systems, _lib
+    from jmolecularenergy_b200.forcefield import _GpuState
+    import torch
+    for s, cutoff, path in ((systems.water_box(200), 0.0, 1), (systems.solvated_chains(3000, chain_fraction=0.3), 8.0, 2)):
+        L = _lib.lib()
+        full = None
+        parts = []
+        for rank, world in ((0, 1), (0, 2), (1, 2)):
+            st = _GpuState(s)
+            st.check(L.jme_set_options(st.h, cutoff, 1.0, 0))
+            st.check(L.jme_set_path(st.h, path))
+            st.check(L.jme_set_shard(st.h, rank, world))
+            st.sync_coords(s.xyz)
+            n_out = L.jme_eval_out_size(st.h, 1)
+            out = torch.zeros(n_out, dtype=torch.float64, device="cuda")
+            st.check(L.jme_set_stream(st.h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            st.check(L.jme_eval_device(st.h, 1, C.c_void_p(out.data_ptr())))
+            torch.cuda.synchronize()
+            if world == 1:
+                full = out.cpu().numpy()
+            else:
+                parts.append(out.cpu().numpy())
+            st.close()
+        summed = parts[0] + parts[1]
+        assert summed[8] == full[8]
+        np.testing.assert_allclose(summed[:8], full[:8], rtol=1e-12, atol=1e-9)
+        np.testing.assert_allclose(summed[10:], full[10:], rtol=1e-9, atol=1e-9 * np.abs(full[10:]).max())
+
+
+def test_gradient_descent_minimizer_matches_oracle_driven_loop(oracle):
+    """The reference's GradientDescentMinimizer loop (restated in jmolecularenergy_b200/minimizer.py) driven
+    by the GPU force field vs the same loop driven by the oracle energy: same accepted energies."""
+    from jmolecularenergy_b200 import GradientDescentMinimizer, systems
+
+    class OracleFF:
+        def calculateEnergy(self, c):
+            return oracle.evaluate(c)["total"]
+
+    a, b = systems.water_box(4), systems.water_box(4)
+    ff = gpu_ff()
+    ff.assignParameters(a)
+    log_a, log_b = [], []
+    m1 = GradientDescentMinimizer(ff)
+    m1.setOnStepConsumer(lambda step, e: log_a.append(e))
+    m1.minimize(a, 3, 0.01, 1e-4)
+    m2 = GradientDescentMinimizer(OracleFF())
+    m2.setOnStepConsumer(lambda step, e: log_b.append(e))
+    m2.minimize(b, 3, 0.01, 1e-4)
+    assert m1.energyCalls == m2.energyCalls == 1 + 4 * 36
+    np.testing.assert_allclose(log_a, log_b, rtol=1e-9)
+    np.testing.assert_allclose(a.xyz, b.xyz, atol=1e-9)
+    assert log_a[-1] < log_a[0]
+
+
+def test_fp64_peak_probe():
+    from jmolecularenergy_b200 import measure_fp64_peak
+    tflops, mhz = measure_fp64_peak()
+    assert 5.0 < tflops < 80.0
