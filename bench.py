@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py - nonbonded pair-interactions/sec (energy + forces) of the MMFF94 hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ions1m|water3k|solvated25k] [--impl reference]
+
+A "step" is one full energy + gradient evaluation of the workload from fresh coordinates: AoS->SoA
+marshalling, (cell build + sort on the cutoff path), nonbonded pair kernel, bonded kernel, final
+reduction and - for N > 1 - the NCCL all-reduce of the packed [energies, gradient] buffer.  Prints ONE JSON
+line on rank 0 (contract in the task description).
+
+Default workload: BASELINE.json config 5 ("1M-atom LJ+Coulomb box, atom-row sharded at 1/2/4/8 GPUs"), the
+configuration the metric "pair-interactions/sec at 1/2/4/8 B200" is quoted on; it fits one GPU, so it is the
+N = 1 workload as well (strong scaling: total work fixed as N grows).  --workload selects config 2
+(water3k, all-pairs tiles) or config 3 (solvated25k, cutoff 10 A).
+
+`value`   : device-resident throughput (coordinates already in HBM), CUDA events on the launching stream.
+`e2e`     : the same metric through the host-buffer C ABI (jme_set_coords + jme_energy_gradient from/to pinned
+            host memory), host wall clock between device synchronisations.
+`roofline`: dominant kernel vs the measured FP64 FMA-pipe peak (this path is FP64-bound, not HBM- or
+            tensor-bound - BASELINE.md section 3); `roofline_hbm` gives the same kernel against measured HBM.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_PAIR = 49.0            # energy + gradient
+METRIC = "nonbonded pair-interactions/sec (energy+forces)"
+UNIT = "pairs/s"
+
+WORKLOADS = {
+    # name: (builder kwargs, cutoff, path, description, algorithmic bytes)
+    "ions1m": dict(cutoff=10.0, path="cells", desc="config 5: 10^6 Na+/Cl- ions, jittered 100^3 lattice, cutoff 10 A, cell-list path"),
+    "water3k": dict(cutoff=0.0, path="allpairs", desc="config 2: 1000 waters (3000 atoms), no cutoff, all-pairs tiles, bonded terms included"),
+    "solvated25k": dict(cutoff=10.0, path="cells", desc="config 3: ~25k atoms (chains + water), cutoff 10 A, cell-list path, exclusions + 1-4"),
+}
+
+
+def build_system(name: str, scale: float = 1.0):
+    from jmolecularenergy_b200 import systems
+    if name == "ions1m":
+        return systems.ion_box(max(4, int(round(100 * scale ** (1.0 / 3.0)))))
+    if name == "water3k":
+        return systems.water_box(max(1, int(1000 * scale)))
+    if name == "solvated25k":
+        return systems.solvated_chains(max(300, int(24999 * scale)), exact_cutoff_pairs=100, cutoff=10.0)
+    raise SystemExit(f"unknown workload {name}")
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """SM clock / throttle reasons sampled with NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_baseline(workload: str, faithful: bool, budget_s: float = 20.0):
+    """The oracle port timed on the host cores on a bounded sample of the workload (about 10-30 s of CPU
+    work): OpenMP over all threads, type-pair table (`faithful`=False) or the reference's per-pair
+    recomputation of R*, eps (`faithful`=True)."""
+    from oracle import oracle
+    threads = oracle.num_threads()
+    cfg = WORKLOADS[workload]
+    # size the sample from a quick probe
+    scale = {"ions1m": 0.05, "water3k": 1.0, "solvated25k": 1.0}[workload]
+    s = build_system(workload, scale)
+    t0 = time.perf_counter()
+    r = oracle.fast_evaluate(s, cutoff=cfg["cutoff"], gradient=True, threads=threads, faithful_constants=faithful)
+    dt = time.perf_counter() - t0
+    rate = r["pairs"] / dt
+    if workload == "ions1m" and dt < budget_s / 8:
+        scale = min(1.0, scale * min(8.0, (budget_s / 2) / max(dt, 1e-3)))
+        s = build_system(workload, scale)
+        t0 = time.perf_counter()
+        r = oracle.fast_evaluate(s, cutoff=cfg["cutoff"], gradient=True, threads=threads, faithful_constants=faithful)
+        dt = time.perf_counter() - t0
+        rate = r["pairs"] / dt
+    return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{s.name}: {r['pairs']} pairs, energy+gradient, {dt:.2f} s, "
+                      f"{'per-pair R*/eps recomputation like the reference' if faithful else 'type-pair table'}; "
+                      "the Java reference itself cannot run (no JVM in the image)"}, s, r
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port, per-pair constants like the Java code)
+    on all host threads; each step is one evaluation of a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+    cfg = WORKLOADS[args.workload]
+    threads = oracle.num_threads()
+    scale = {"ions1m": 0.03, "water3k": 1.0, "solvated25k": 0.5}[args.workload]
+    s = build_system(args.workload, scale)
+    times, pairs = [], 0
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        r = oracle.fast_evaluate(s, cutoff=cfg["cutoff"], gradient=True, threads=threads, faithful_constants=True)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+            pairs = r["pairs"]
+    total = sum(times)
+    value = pairs * len(times) / total
+    sample = f"{s.name}: {pairs} pairs per step (bounded sample of {args.workload}), OpenMP x{threads}, per-pair R*/eps like MMFF94VdwComponent.java:106-135"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "description": cfg["desc"], "cutoff": cfg["cutoff"], "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="ions1m", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from jmolecularenergy_b200 import _lib, measure_fp64_peak
+    from jmolecularenergy_b200.distributed import ShardedMMFF94, unpack
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+
+    cfg = WORKLOADS[args.workload]
+    system = build_system(args.workload)
+    n = system.n_atoms
+    L = _lib.lib()
+    ev = ShardedMMFF94(system, cutoff=cfg["cutoff"], path=cfg["path"], rank=rank, world=world)
+    st = ev.state
+    xyz_dev = torch.from_numpy(system.xyz).to(dev)
+    out = ev.new_output(True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    def step_device():
+        ev.set_coords(xyz_dev)            # AoS -> SoA on the device; invalidates the cell sort
+        ev.evaluate_into(out, True)       # kernels (+ all-reduce) on the current stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    res = unpack(out.cpu().numpy(), n, True)
+    pairs = res["pairs"]
+
+    # ---- timed region: K steps, each bracketed by CUDA events on the launching stream, L2 flushed between
+    L.jme_set_profiling(st.h, 1)
+    sampler = ClockSampler(local_rank)
+    launches0 = ev.launch_count()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(k & 0xff)
+        starts[k].record()
+        step_device()
+        stops[k].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = ev.launch_count() - launches0
+    ms = [starts[k].elapsed_time(stops[k]) for k in range(args.steps)]
+    total_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    nb = (C.c_float * args.steps)()
+    bl = (C.c_float * args.steps)()
+    got = C.c_int()
+    L.jme_profile_read(st.h, nb, bl, args.steps, C.byref(got))
+    L.jme_set_profiling(st.h, 0)
+    nb_ms = float(np.mean(nb[:got.value])) if got.value else float("nan")
+    build_ms = float(np.mean(bl[:got.value])) if got.value else float("nan")
+
+    # ---- end to end through the host-buffer C ABI (rank-local; for N > 1 the partial results are reduced
+    #      on the device and copied back, so the host round trip is included on every rank)
+    host_xyz = torch.from_numpy(system.xyz.copy()).pin_memory()
+    host_out = torch.empty(ev.n_out_grad, dtype=torch.float64).pin_memory()
+    total_e = C.c_double()
+    comps = (C.c_double * 7)()
+
+    def step_e2e():
+        if world == 1:
+            st.check(L.jme_set_coords(st.h, host_xyz.data_ptr(), n))
+            st.check(L.jme_energy_gradient(st.h, C.byref(total_e), comps, host_out.data_ptr() + 80))
+        else:
+            st.check(L.jme_set_coords(st.h, host_xyz.data_ptr(), n))
+            ev.evaluate_into(out, True)
+            host_out.copy_(out, non_blocking=True)
+            torch.cuda.synchronize()
+
+    e2e_steps = max(5, min(args.steps, 30))
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        fp64_tflops, fp64_mhz = measure_fp64_peak()
+        ms_per_step = total_ms / args.steps
+        value = pairs / (ms_per_step * 1e-3)
+        # dominant kernel: the nonbonded pair kernel of this rank's shard
+        local_pairs = pairs / world
+        achieved_tf = FLOP_PER_PAIR * local_pairs / (nb_ms * 1e-3) / 1e12
+        if cfg["path"] == "cells":
+            alg_bytes = 4.0 * local_pairs + 84.0 * n / world          # 4 B/pair + 84 B/atom
+        else:
+            alg_bytes = 36.0 / 128.0 * local_pairs
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = json.load(fh).get(args.workload)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "description": cfg["desc"], "atoms": n, "pairs_per_step": pairs,
+                       "cutoff": cfg["cutoff"], "path": cfg["path"], "parallelism": f"atom-row shards x{world} + all-reduce" if world > 1 else "single GPU",
+                       "l2": "256 MiB written between timed steps (L2 flush); step = marshal + cell build + pairs + bonded + reduce"},
+            "e2e": {"value": pairs / (e2e_s / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": 24 * n,
+                    "d2h_bytes_per_step": 24 * n + 80, "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_tflops, "unit": "TFLOP/s",
+                         "frac": achieved_tf / fp64_tflops, "traffic": traffic,
+                         "kernel": "cells_pair_kernel<GRAD>" if cfg["path"] == "cells" else "ap_kernel<GRAD>",
+                         "kernel_ms": nb_ms, "build_ms": build_ms,
+                         "peak_source": f"DFMA chain microbenchmark measured in this run ({fp64_mhz:.0f} MHz equivalent at 64 FMA/clk/SM); "
+                                        "MEASURED_PEAKS.json has no FP64 figure",
+                         "flop_per_pair": FLOP_PER_PAIR},
+            "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / (nb_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"),
+                             "unit": "GB/s", "frac": alg_bytes / (nb_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs"),
+                             "peak_source": f"MEASURED_PEAKS.json ({peak_kind})"},
+            "wall_s_timed_region": t_wall,
+            "energy_kcal_mol": res["total"],
+        }
+        if not args.no_cpu_baseline:
+            base, _, _ = cpu_baseline(args.workload, faithful=False)
+            line["cpu_baseline"] = base
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ev.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -133,10 +133,12 @@ int jme_pair_list(jme_handle_t* h, int32_t* pair_i, int32_t* pair_j, uint8_t* is
                   int64_t* n_pairs);
 
 /* ---- device-resident entry points (multi-GPU plumbing and HBM-resident benchmarking) ----
- * All work is enqueued on `stream` (a cudaStream_t passed as void*, NULL = the handle's own stream);
+ * All work is enqueued on `stream`: a cudaStream_t passed as void* - NULL is the legacy default stream,
+ * JME_STREAM_OWN selects the handle's own non-blocking stream again (the state after jme_create);
  * nothing is synchronised.  d_xyz: device AoS [n_atoms][3].  d_out: device doubles
- * [0]=total [1..7]=components [8]=pairs evaluated (as double) [9..9+3n) gradient AoS (only when
- * want_gradient).  This is the buffer a multi-GPU caller all-reduces. */
+ * [0]=total [1..7]=components [8]=pairs evaluated [9]=pairs candidate (both as double)
+ * [10..10+3n) gradient AoS (only when want_gradient).  This is the buffer a multi-GPU caller all-reduces. */
+#define JME_STREAM_OWN ((void*)(intptr_t)-1)
 int jme_set_stream(jme_handle_t* h, void* stream);
 int jme_set_coords_device(jme_handle_t* h, const double* d_xyz, int64_t n_atoms);
 int jme_eval_device(jme_handle_t* h, int want_gradient, double* d_out);
@@ -144,6 +146,13 @@ int64_t jme_eval_out_size(const jme_handle_t* h, int want_gradient);   /* double
 
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 uint64_t jme_launch_count(const jme_handle_t* h);
+
+/* Kernel timing for the roofline: when on, every evaluation records CUDA events (on the launching
+ * stream) before the cell build, before and after the nonbonded pair kernel.  jme_profile_read (call it
+ * after the stream is synchronised) returns the per-evaluation durations recorded since the last read:
+ * nonbonded_ms[k] = pair kernel, build_ms[k] = cell build + sort (0 on the all-pairs path). */
+int jme_set_profiling(jme_handle_t* h, int on);
+int jme_profile_read(jme_handle_t* h, float* nonbonded_ms, float* build_ms, int capacity, int* n_read);
 
 /* FP64 FMA-pipe peak of the current device measured with a dependent-chain DFMA kernel:
  * returns TFLOP/s (2 flop per FMA) through *tflops. */

@@ -12,14 +12,15 @@ import os
 from ._abi import JmeSystem, c_f64p, c_i32p, c_i64p, c_u8p, c_u64p
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libjme_b200.so")
+# JME_B200_LIB lets kernel-tuning experiments load an alternative build of the SAME library
+LIB_PATH = os.environ.get("JME_B200_LIB") or os.path.join(PKG_DIR, "libjme_b200.so")
 
 EXPORTS = (
     "jme_abi_version", "jme_last_create_error", "jme_create", "jme_destroy", "jme_last_error",
     "jme_set_options", "jme_set_path", "jme_set_shard", "jme_set_coords", "jme_set_coord1", "jme_get_coords",
     "jme_energy", "jme_energy_gradient", "jme_pair_stats", "jme_pair_list", "jme_set_stream",
     "jme_set_coords_device", "jme_eval_device", "jme_eval_out_size", "jme_launch_count",
-    "jme_measure_fp64_peak", "jme_enumerate_terms", "jme_exclusions",
+    "jme_measure_fp64_peak", "jme_enumerate_terms", "jme_exclusions", "jme_set_profiling", "jme_profile_read",
 )
 
 _lib = None
@@ -79,6 +80,10 @@ def lib():
     L.jme_launch_count.argtypes = [H]
     L.jme_measure_fp64_peak.restype = C.c_int
     L.jme_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.jme_set_profiling.restype = C.c_int
+    L.jme_set_profiling.argtypes = [H, C.c_int]
+    L.jme_profile_read.restype = C.c_int
+    L.jme_profile_read.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]
     L.jme_enumerate_terms.restype = C.c_int
     L.jme_enumerate_terms.argtypes = [C.c_int64, c_i32p, c_u8p, C.c_int64, c_i32p, c_i32p,
                                       c_i32p, c_i64p, c_i32p, c_i64p, c_i32p, c_i64p]

@@ -81,6 +81,12 @@ struct jme_handle {
     double* d_out = nullptr;
     double* h_out = nullptr;   // pinned header
     uint64_t last_pairs = 0, last_cand = 0;
+
+    // profiling ring: 3 events per evaluation (before build, before pairs, after pairs)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;
+    size_t prof_used = 0;     // evaluations recorded since the last read
+    ~jme_handle() { for (cudaEvent_t e : prof_events) cudaEventDestroy(e); }
 };
 
 namespace {
@@ -318,6 +324,19 @@ int ensure_plan(jme_handle* h) {
     return JME_OK;
 }
 
+constexpr size_t kProfRing = 4096;
+
+// returns the 3 events of the next profiling slot, or nullptr when profiling is off / the ring is full
+cudaEvent_t* prof_slot(jme_handle* h) {
+    if (!h->profiling || h->prof_used >= kProfRing) return nullptr;
+    while (h->prof_events.size() < 3 * (h->prof_used + 1)) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        h->prof_events.push_back(e);
+    }
+    return &h->prof_events[3 * h->prof_used];
+}
+
 size_t ap_smem_bytes(const DeviceSystem& ds) {
     return (size_t)ds.n_types * ds.n_types * sizeof(PairConst) + kApWarps * (4 * 32 + 16) * sizeof(double);
 }
@@ -345,17 +364,23 @@ int enqueue_eval(jme_handle* h, bool grad, double* d_out_user) {
     const bool cut = h->cutoff > 0;
     ReduceArgs A{};
     A.n = h->ds.n; A.n_pad = h->ds.n_pad;
+    cudaEvent_t* pe = prof_slot(h);
+    if (pe) cudaEventRecord(pe[0], h->stream);
     if (h->active_path == JME_PATH_ALLPAIRS) {
+        if (pe) cudaEventRecord(pe[1], h->stream);
         if (grad) rc = cut ? launch_ap<true, true>(h) : launch_ap<true, false>(h);
         else rc = cut ? launch_ap<false, true>(h) : launch_ap<false, false>(h);
         if (rc) return rc;
         A.gpart = h->d_gpart; A.n_slots = h->n_slots; A.direct = nullptr;
         A.epart = h->d_epart; A.cpart = h->d_cpart; A.n_epart = h->n_epart;
     } else {
+        if ((rc = run_cell_sort(h->cells, h->ds, h->stream, h->launches, h->err))) return rc;
+        if (pe) cudaEventRecord(pe[1], h->stream);
         if ((rc = run_cell_path(h->cells, h->ds, grad, h->stream, h->launches, h->err))) return rc;
         A.gpart = nullptr; A.n_slots = 0; A.direct = h->cells.d_grad;
         A.epart = h->cells.d_epart; A.cpart = h->cells.d_cpart; A.n_epart = h->cells.n_epart;
     }
+    if (pe) { cudaEventRecord(pe[2], h->stream); ++h->prof_used; }
     const long long n_terms = h->term_end - h->term_begin;
     if (n_terms > 0) {
         if (grad) bonded_kernel<true><<<h->n_bpart, kBondedThreads, 0, h->stream>>>(h->ds, h->bt, h->term_begin, h->term_end, h->d_slots, h->d_bpart);
@@ -509,7 +534,8 @@ int jme_set_shard(jme_handle_t* h, int rank, int world) {
 
 int jme_set_stream(jme_handle_t* h, void* stream) {
     if (!h) return JME_ERR_INVALID;
-    h->stream = stream ? static_cast<cudaStream_t>(stream) : h->own_stream;
+    // NULL is a real stream (the legacy default stream, which is what torch's default stream is)
+    h->stream = (stream == JME_STREAM_OWN) ? h->own_stream : static_cast<cudaStream_t>(stream);
     return JME_OK;
 }
 
@@ -643,6 +669,30 @@ int jme_pair_list(jme_handle_t* h, int32_t* pair_i, int32_t* pair_j, uint8_t* is
     if (ce != cudaSuccess) return fail(h, JME_ERR_CUDA, std::string("pair list: ") + cudaGetErrorString(ce));
     *n_pairs = (int64_t)cnt;
     return rc;
+}
+
+int jme_set_profiling(jme_handle_t* h, int on) {
+    if (!h) return JME_ERR_INVALID;
+    h->profiling = on != 0;
+    h->prof_used = 0;
+    return JME_OK;
+}
+
+int jme_profile_read(jme_handle_t* h, float* nonbonded_ms, float* build_ms, int capacity, int* n_read) {
+    if (!h || !n_read || capacity < 0) return JME_ERR_INVALID;
+    const size_t m = std::min<size_t>(h->prof_used, (size_t)capacity);
+    for (size_t k = 0; k < m; ++k) {
+        cudaEvent_t* e = &h->prof_events[3 * k];
+        float a = 0, b = 0;
+        JME_CUDA(h, cudaEventSynchronize(e[2]));
+        JME_CUDA(h, cudaEventElapsedTime(&a, e[0], e[1]));
+        JME_CUDA(h, cudaEventElapsedTime(&b, e[1], e[2]));
+        if (build_ms) build_ms[k] = a;
+        if (nonbonded_ms) nonbonded_ms[k] = b;
+    }
+    *n_read = (int)m;
+    h->prof_used = 0;
+    return JME_OK;
 }
 
 int jme_measure_fp64_peak(double* tflops, double* sm_clock_mhz_estimate) {

@@ -14,7 +14,8 @@
 //      them with all lanes busy: exact FP64 predicate (bit-identical to the reference's
 //      sqrt(dx*dx+dy*dy+dz*dz) > cutoff via the r^2 threshold), exclusion / 1-4 lookup, vdW + Coulomb.
 //      Each pair is evaluated from both of its atoms (no Newton's third law): no scatter, no atomics,
-//      deterministic; energies are halved.
+//      deterministic; energies are halved.  The row ranges of an atom are computed lane-parallel (one
+//      lane per neighbour cell row, culled against the cutoff sphere in FP32 with padded margins).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -27,7 +28,13 @@
 
 namespace jme {
 
-constexpr int kCellWarps = 8;
+#ifndef JME_CELL_WARPS
+#define JME_CELL_WARPS 8
+#endif
+#ifndef JME_CELL_MIN_BLOCKS
+#define JME_CELL_MIN_BLOCKS 3
+#endif
+constexpr int kCellWarps = JME_CELL_WARPS;
 constexpr int kCellThreads = kCellWarps * 32;
 constexpr int kScanBlock = 1024;          // elements per scan block
 
@@ -38,6 +45,7 @@ struct GridParams {
     int reach;               // neighbour cells to visit per direction: ceil(cutoff / edge)
     float r2f_max;           // conservative FP32 candidate threshold on r^2
     double cutoff_pad;       // cutoff + margin used for row culling
+    float edge_f, inv_edge_f, cut2_pad_f;   // FP32 copies for the per-row culling (margins included)
 };
 
 struct CellArrays {
@@ -51,8 +59,9 @@ struct CellArrays {
     int* order_tmp;          // [n]
     int* orig;               // [n] sorted position -> original atom
     int* scell;              // [n] cell of sorted position
-    double *sx, *sy, *sz, *sq;
-    float *fx, *fy, *fz;
+    double2* sxy;            // [n] sorted x, y   } two 16-byte records per atom: a gather of either touches
+    double2* szq;            // [n] sorted z, q   } half the cache lines a 32-byte record would
+    float4* fxyz;            // [n] sorted positions relative to the grid origin, FP32 (w unused)
     int* stype;
     const long long* excl_ptr;    // CSR over original atom index
     const unsigned int* excl_ent;
@@ -115,6 +124,12 @@ __global__ void grid_setup_kernel(const double* __restrict__ part, int n_part, d
     const double rpad = cutoff + dr;
     g->r2f_max = (float)(rpad * rpad * (1.0 + 1e-6)) * (1.0f + 4e-7f);
     g->cutoff_pad = cutoff + 2.0 * dr + 1e-6;
+    // row culling runs in FP32 on origin-relative coordinates: pad by the FP32 coordinate / cell-boundary
+    // error once more, and round every FP32 constant in the conservative direction
+    const double cpad = g->cutoff_pad + 4.0 * dr;
+    g->edge_f = (float)edge;
+    g->inv_edge_f = (float)(1.0 / edge);
+    g->cut2_pad_f = (float)(cpad * cpad) * (1.0f + 4e-7f);
 }
 
 // ---- 2. binning --------------------------------------------------------------------------------
@@ -218,12 +233,10 @@ __global__ void cell_rank_gather_kernel(DeviceSystem S, CellArrays C) {
     C.orig[d] = a;
     C.scell[d] = c;
     const double x = S.x[a], y = S.y[a], z = S.z[a];
-    C.sx[d] = x; C.sy[d] = y; C.sz[d] = z;
-    C.sq[d] = S.q[a];
+    C.sxy[d] = make_double2(x, y);
+    C.szq[d] = make_double2(z, S.q[a]);
     C.stype[d] = S.type[a];
-    C.fx[d] = (float)(x - g->ox);
-    C.fy[d] = (float)(y - g->oy);
-    C.fz[d] = (float)(z - g->oz);
+    C.fxyz[d] = make_float4((float)(x - g->ox), (float)(y - g->oy), (float)(z - g->oz), 0.0f);
 }
 
 // ---- 4. pairs ----------------------------------------------------------------------------------
@@ -236,15 +249,21 @@ struct CellPairArgs {
     int* out_i; int* out_j; unsigned char* out_14; long long capacity; unsigned long long* cursor;
 };
 
+constexpr int kQueue = 128;          // per-warp candidate ring (power of two)
+
 template <bool GRAD, bool EMIT>
-__global__ void __launch_bounds__(kCellThreads, 2)
+__global__ void __launch_bounds__(kCellThreads, JME_CELL_MIN_BLOCKS)
 cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PairConst* s_table = reinterpret_cast<PairConst*>(smem_raw);
     const int TT = S.n_types * S.n_types;
     unsigned int* s_queue = reinterpret_cast<unsigned int*>(s_table + TT);
+    int2* s_rows = reinterpret_cast<int2*>(s_queue + kCellWarps * kQueue);
+    unsigned int* s_excl = reinterpret_cast<unsigned int*>(s_rows + kCellWarps * 32);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned int* queue = s_queue + warp * 64;
+    unsigned int* queue = s_queue + warp * kQueue;
+    int2* rows = s_rows + warp * 32;
+    unsigned int* excl = s_excl + warp * 32;
     for (int t = threadIdx.x; t < TT; t += kCellThreads) s_table[t] = S.table[t];
     __syncthreads();
 
@@ -252,55 +271,110 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
     const int gw = blockIdx.x * kCellWarps + warp;
     const int n_warps = gridDim.x * kCellWarps;
     const unsigned int lt_mask = (1u << lane) - 1u;
-    const double cut2 = g.cutoff_pad * g.cutoff_pad;
+    const int width = 2 * g.reach + 1;
+    const int n_rows = width * width;          // <= 25: reach <= 2 by construction (edge >= cutoff / 2)
+    const double2* __restrict__ sxy = C.sxy;
+    const double2* __restrict__ szq = C.szq;
+    const float4* __restrict__ fxyz = C.fxyz;
+    const int* __restrict__ stype = C.stype;
+    const int* __restrict__ orig = C.orig;
 
     double ev_w = 0, ee_w = 0;
     unsigned long long n_eval_w = 0, n_cand_w = 0;
 
     for (int i = P.i_begin + gw; i < P.i_end; i += n_warps) {
-        const double xi = C.sx[i], yi = C.sy[i], zi = C.sz[i];
-        const float fxi = C.fx[i], fyi = C.fy[i], fzi = C.fz[i];
-        const double qi = S.ele_scale * C.sq[i];
-        const PairConst* trow = s_table + C.stype[i] * S.n_types;
-        const int oi = C.orig[i];
-        const long long eb = C.excl_ptr[oi], een = C.excl_ptr[oi + 1];
+        const double2 pi_xy = sxy[i], pi_zq = szq[i];
+        const float4 fi = fxyz[i];
+        const double qi2 = 2.0 * S.ele_scale * pi_zq.y;      // doubled energies, see pair_terms
+        const PairConst* trow = s_table + stype[i] * S.n_types;
+        const int oi = orig[i];
+        const long long eb = C.excl_ptr[oi];
+        const int n_excl = (int)(C.excl_ptr[oi + 1] - eb);
         const int ci = C.scell[i];
         const int cx = ci % g.nx, cy = (ci / g.nx) % g.ny, cz = ci / (g.nx * g.ny);
 
+        // ---- lane-parallel: the candidate range of neighbour cell row `lane`, culled against the sphere
+        {
+            int jb = 0, je = 0;
+            if (lane < n_rows) {
+                const int ddy = lane % width - g.reach, ddz = lane / width - g.reach;
+                const int y2 = cy + ddy, z2 = cz + ddz;
+                if (y2 >= 0 && y2 < g.ny && z2 >= 0 && z2 < g.nz) {
+                    // distance from the atom to the cell slabs y2 / z2 (0 inside), origin-relative FP32
+                    float my = 0.f, mz = 0.f;
+                    if (ddy > 0) my = y2 * g.edge_f - fi.y; else if (ddy < 0) my = fi.y - (y2 + 1) * g.edge_f;
+                    if (ddz > 0) mz = z2 * g.edge_f - fi.z; else if (ddz < 0) mz = fi.z - (z2 + 1) * g.edge_f;
+                    my = fmaxf(my, 0.f);
+                    mz = fmaxf(mz, 0.f);
+                    const float rem = g.cut2_pad_f - (my * my + mz * mz);
+                    if (rem >= 0.f) {
+                        const float xr = sqrtf(rem) * (1.0f + 1e-6f);
+                        int x0 = (int)floorf((fi.x - xr) * g.inv_edge_f - 1e-4f);
+                        int x1 = (int)floorf((fi.x + xr) * g.inv_edge_f + 1e-4f);
+                        x0 = max(max(x0, cx - g.reach), 0);
+                        x1 = min(min(x1, cx + g.reach), g.nx - 1);
+                        if (x0 <= x1) {
+                            const int row = (z2 * g.ny + y2) * g.nx;
+                            jb = C.start[row + x0];
+                            je = C.start[row + x1 + 1];
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            rows[lane] = make_int2(jb, je);
+            if (n_excl > 0) excl[lane] = lane < n_excl ? C.excl_ent[eb + lane] : 0xffffffffu;
+            __syncwarp();
+        }
+
         double gix = 0, giy = 0, giz = 0, ev = 0, ee = 0;
         unsigned int n_eval = 0, n_cand = 0;
-        int qn = 0;
+        unsigned int q_head = 0, q_tail = 0;       // ring indices (monotonic; entries at index & (kQueue-1))
 
-        // evaluates queue[0..m) with lane l taking entry l
+        // ---- heavy stage: the 32 (or, at the end, fewer) oldest queue entries, lane l taking entry l
         auto process = [&](int m) {
             const bool active = lane < m;
-            const unsigned int ent = active ? queue[lane] : 0u;
-            const int j = active ? (int)ent : i;
-            const double dx = xi - C.sx[j], dy = yi - C.sy[j], dz = zi - C.sz[j];
+            const int j = active ? (int)queue[(q_head + lane) & (kQueue - 1)] : i;
+            q_head += m;
+            const double2 pj_xy = sxy[j], pj_zq = szq[j];
+            const int tj = stype[j];
+            const double dx = pi_xy.x - pj_xy.x, dy = pi_xy.y - pj_xy.y, dz = pi_zq.x - pj_zq.x;
             // strict double, left-to-right, no FMA: Point3d.distance squared
             const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
             bool on = active && !(r2 > S.r2_max);
             bool f14 = false;
-            const int oj = C.orig[j];
-            for (long long e = eb; e < een; ++e) {          // warp-uniform list of atom i
-                const unsigned int x = C.excl_ent[e];
-                if ((int)(x & ~kFlag14) == oj) {
-                    if (x & kFlag14) f14 = true; else on = false;
+            bool counted = on && j > i;            // each unordered pair is counted from its lower sorted index
+            int oj = 0;
+            if (EMIT) oj = orig[j];
+            if (n_excl > 0) {                       // warp-uniform: the list belongs to atom i
+                if (!EMIT) oj = orig[j];
+                const int n_sm = min(n_excl, 32);
+                for (int e = 0; e < n_sm; ++e) {
+                    const unsigned int x = excl[e];
+                    if ((int)(x & ~kFlag14) == oj) {
+                        if (x & kFlag14) f14 = true; else on = false;
+                    }
                 }
+                for (int e = 32; e < n_excl; ++e) {
+                    const unsigned int x = C.excl_ent[eb + e];
+                    if ((int)(x & ~kFlag14) == oj) {
+                        if (x & kFlag14) f14 = true; else on = false;
+                    }
+                }
+                counted = on && j > i;
             }
-            const bool counted = on && oj > oi;
             n_eval += __popc(__ballot_sync(0xffffffffu, counted));
             if (EMIT) {
                 if (counted) {
                     const unsigned long long p = atomicAdd(P.cursor, 1ull);
-                    if ((long long)p < P.capacity) { P.out_i[p] = oi; P.out_j[p] = oj; P.out_14[p] = f14; }
+                    if ((long long)p < P.capacity) { P.out_i[p] = min(oi, oj); P.out_j[p] = max(oi, oj); P.out_14[p] = f14; }
                 }
             } else {
-                double qq = qi * C.sq[j];
-                if (f14) qq *= kEle14;
-                const bool tiny = __double2hiint(r2) < 0x00100000;
+                double qq2 = qi2 * pj_zq.y;
+                if (f14) qq2 *= kEle14;
+                // coincident atoms: keep the (finite) buffered energy, no gradient direction exists
                 double e1, e2, f;
-                pair_terms<GRAD>((on && !tiny) ? r2 : (on ? 1e-300 : 1.0), trow[C.stype[j]], qq, e1, e2, f);
+                pair_terms<GRAD>(on ? clamp_r2(r2) : 1.0, trow[tj], qq2, e1, e2, f);
                 ev += on ? e1 : 0.0;
                 ee += on ? e2 : 0.0;
                 if (GRAD) {
@@ -312,54 +386,31 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
             }
         };
 
-        for (int ddz = -g.reach; ddz <= g.reach; ++ddz) {
-            const int z2 = cz + ddz;
-            if (z2 < 0 || z2 >= g.nz) continue;
-            // distance from the atom to the slab of cells z2 (0 inside)
-            double mz = 0;
-            if (ddz > 0) mz = (g.oz + z2 * g.edge) - zi; else if (ddz < 0) mz = zi - (g.oz + (z2 + 1) * g.edge);
-            mz = fmax(mz, 0.0);
-            for (int ddy = -g.reach; ddy <= g.reach; ++ddy) {
-                const int y2 = cy + ddy;
-                if (y2 < 0 || y2 >= g.ny) continue;
-                double my = 0;
-                if (ddy > 0) my = (g.oy + y2 * g.edge) - yi; else if (ddy < 0) my = yi - (g.oy + (y2 + 1) * g.edge);
-                my = fmax(my, 0.0);
-                const double rem = cut2 - (my * my + mz * mz);
-                if (rem < 0) continue;                       // the whole cell row is beyond the cutoff
-                const double xr = sqrt(rem);
-                int x0 = (int)floor((xi - xr - g.ox) * g.inv_edge), x1 = (int)floor((xi + xr - g.ox) * g.inv_edge);
-                x0 = max(max(x0, cx - g.reach), 0);
-                x1 = min(min(x1, cx + g.reach), g.nx - 1);
-                if (x0 > x1) continue;
-                const int row = (z2 * g.ny + y2) * g.nx;
-                const int jb = C.start[row + x0], je = C.start[row + x1 + 1];
-                for (int base = jb; base < je; base += 32) {
-                    const int j = base + lane;
-                    bool hit = false;
-                    if (j < je && j != i) {
-                        const float ax = fxi - C.fx[j], ay = fyi - C.fy[j], az = fzi - C.fz[j];
-                        hit = (ax * ax + ay * ay + az * az) <= g.r2f_max;
-                    }
-                    const unsigned int m = __ballot_sync(0xffffffffu, hit);
-                    if (m == 0) continue;
-                    n_cand += __popc(m);
-                    if (hit) queue[qn + __popc(m & lt_mask)] = (unsigned int)j;
-                    qn += __popc(m);
-                    __syncwarp();
-                    if (qn >= 32) {
-                        process(32);
-                        __syncwarp();
-                        const unsigned int moved = (lane < qn - 32) ? queue[32 + lane] : 0u;
-                        __syncwarp();
-                        if (lane < qn - 32) queue[lane] = moved;
-                        qn -= 32;
-                        __syncwarp();
-                    }
-                }
+        // ---- candidate scan: trips of 64 candidates (two loads in flight) over the culled row ranges
+        for (int r = 0; r < n_rows; ++r) {
+            const int2 rg = rows[r];
+            for (int base = rg.x; base < rg.y; base += 64) {
+                const int j0 = base + lane, j1 = j0 + 32;
+                const float4 a0 = fxyz[min(j0, rg.y - 1)];
+                const float4 a1 = fxyz[min(j1, rg.y - 1)];
+                const float x0 = fi.x - a0.x, y0 = fi.y - a0.y, z0 = fi.z - a0.z;
+                const float x1 = fi.x - a1.x, y1 = fi.y - a1.y, z1 = fi.z - a1.z;
+                const bool h0 = (x0 * x0 + y0 * y0 + z0 * z0) <= g.r2f_max && j0 < rg.y && j0 != i;
+                const bool h1 = (x1 * x1 + y1 * y1 + z1 * z1) <= g.r2f_max && j1 < rg.y && j1 != i;
+                const unsigned int m0 = __ballot_sync(0xffffffffu, h0);
+                const unsigned int m1 = __ballot_sync(0xffffffffu, h1);
+                if ((m0 | m1) == 0) continue;
+                const int c0n = __popc(m0);
+                if (h0) queue[(q_tail + __popc(m0 & lt_mask)) & (kQueue - 1)] = (unsigned int)j0;
+                if (h1) queue[(q_tail + c0n + __popc(m1 & lt_mask)) & (kQueue - 1)] = (unsigned int)j1;
+                q_tail += c0n + __popc(m1);
+                n_cand += c0n + __popc(m1);
+                __syncwarp();
+                while (q_tail - q_head >= 32) process(32);
             }
         }
-        if (qn > 0) { process(qn); __syncwarp(); }
+        if (q_tail != q_head) process((int)(q_tail - q_head));
+        __syncwarp();
 
         if (GRAD && !EMIT) {
             gix = warp_sum(gix);
@@ -377,9 +428,9 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
         n_cand_w += n_cand;
     }
     if (!EMIT) {
-        // every pair was seen from both atoms: half the energy each
-        ev_w = 0.5 * warp_sum(ev_w);
-        ee_w = 0.5 * warp_sum(ee_w);
+        // energies were accumulated doubled (pair_terms) and every pair was seen from both atoms: x 1/4
+        ev_w = 0.25 * warp_sum(ev_w);
+        ee_w = 0.25 * warp_sum(ee_w);
         if (lane == 0) {
             P.epart[2 * gw] = ev_w;
             P.epart[2 * gw + 1] = ee_w;
@@ -429,9 +480,8 @@ inline int build_cell_plan(CellPlan& p, const HostSystem& hs, const DeviceSystem
         bool ok = cell_alloc(p, &a.grid, 1, err) && cell_alloc(p, &a.cell_of, n, err) && cell_alloc(p, &a.count, a.max_cells + 1, err) &&
                   cell_alloc(p, &a.start, a.max_cells + 1, err) && cell_alloc(p, &a.cursor, a.max_cells, err) &&
                   cell_alloc(p, &a.block_sums, scan_blocks, err) && cell_alloc(p, &a.order_tmp, n, err) &&
-                  cell_alloc(p, &a.orig, n, err) && cell_alloc(p, &a.scell, n, err) && cell_alloc(p, &a.sx, n, err) &&
-                  cell_alloc(p, &a.sy, n, err) && cell_alloc(p, &a.sz, n, err) && cell_alloc(p, &a.sq, n, err) &&
-                  cell_alloc(p, &a.fx, n, err) && cell_alloc(p, &a.fy, n, err) && cell_alloc(p, &a.fz, n, err) &&
+                  cell_alloc(p, &a.orig, n, err) && cell_alloc(p, &a.scell, n, err) && cell_alloc(p, &a.sxy, n, err) &&
+                  cell_alloc(p, &a.szq, n, err) && cell_alloc(p, &a.fxyz, n, err) &&
                   cell_alloc(p, &a.stype, n, err) && cell_alloc(p, &a.bbox_part, 6 * (size_t)a.bbox_blocks, err) &&
                   cell_alloc(p, &p.d_grad, 3 * (size_t)ds.n_pad, err);
         if (!ok) return JME_ERR_NOMEM;
@@ -449,7 +499,7 @@ inline int build_cell_plan(CellPlan& p, const HostSystem& hs, const DeviceSystem
         // persistent-style launch: enough warps to fill the chip, grid-stride over atoms
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-        p.grid_pairs = std::max(1, std::min((n + kCellWarps - 1) / kCellWarps, sms * 8));
+        p.grid_pairs = std::max(1, std::min((n + kCellWarps - 1) / kCellWarps, sms * 12));
         p.n_epart = p.grid_pairs * kCellWarps;
         if (!cell_alloc(p, &p.d_epart, 2 * (size_t)p.n_epart, err) || !cell_alloc(p, &p.d_cpart, 2 * (size_t)p.n_epart, err)) return JME_ERR_NOMEM;
         p.built = true;
@@ -466,7 +516,8 @@ inline int build_cell_plan(CellPlan& p, const HostSystem& hs, const DeviceSystem
 }
 
 inline size_t cells_smem_bytes(const DeviceSystem& ds) {
-    return (size_t)ds.n_types * ds.n_types * sizeof(PairConst) + kCellWarps * 64 * sizeof(unsigned int);
+    return (size_t)ds.n_types * ds.n_types * sizeof(PairConst) +
+           kCellWarps * (kQueue * sizeof(unsigned int) + 32 * sizeof(int2) + 32 * sizeof(unsigned int));
 }
 
 #define JME_CELL_CHECK()                                                                           \

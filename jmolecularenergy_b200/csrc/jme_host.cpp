@@ -169,7 +169,7 @@ std::string build_host_system(const jme_system_t* s, HostSystem& h) {
             pc.c2 = 0.07 * R;                                 // :140
             pc.c3 = 1.12 * R7;                                // :141
             pc.c4 = 0.12 * R7;                                // :141
-            pc.k1 = eps * std::pow(1.07 * R, 7);              // eps (1.07 R*)^7, folded numerator of :140
+            pc.k1 = 2.0 * (eps * std::pow(1.07 * R, 7));      // 2 eps (1.07 R*)^7: folded numerator of :140, doubled (pair_terms)
             h.pair_table[(size_t)a * T + b] = h.pair_table[(size_t)b * T + a] = pc;
             h.pair_rstar[(size_t)a * T + b] = h.pair_rstar[(size_t)b * T + a] = R;
             h.pair_eps[(size_t)a * T + b] = h.pair_eps[(size_t)b * T + a] = eps;

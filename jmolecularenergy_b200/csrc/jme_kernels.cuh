@@ -69,8 +69,80 @@ __device__ __forceinline__ double warp_sum(double v) {
 // gpart layout: [slot][3][n_pad].  Slot I (< n_blocks) receives the j-side gradients produced by the
 // items of i-block I; slot n_blocks + c receives the i-side gradients of chunk c of every row.  Each
 // (slot, atom) has exactly one writer, so the later fixed-order sum is deterministic.
+// r2 with its exponent clamped from below (integer max on the high word): coincident atoms (r2 == 0) keep
+// their finite buffered energy and get no gradient (f * dx = 0), without a NaN from 1/sqrt(0)
+__device__ __forceinline__ double clamp_r2(double r2) {
+    return __hiloint2double(max(__double2hiint(r2), 0x01a00000), __double2loint(r2));
+}
+
+// One 32x32 tile.  Lane l owns i-atom l of the row block; at step k it meets j-atom (l + k) & 31 of the
+// staged tile, so every step touches 32 distinct j atoms and the j-side accumulator that travels with
+// atom (l + k) is handed from lane l+1 to lane l between steps (warp shuffle).
+//   MASKED = false : plain off-diagonal tile, all 1024 pairs interact - no predicate, no selects
+//   MASKED = true  : diagonal tile (offsets 1..16, offset 16 from lanes < 16 only) and/or exclusion,
+//                    1-4 and padding bit masks
+template <bool GRAD, bool CUTOFF, bool MASKED>
+__device__ __forceinline__ void ap_tile(const double xi, const double yi, const double zi, const double qi2,
+                                        const PairConst* __restrict__ trow, const double* __restrict__ sx,
+                                        const double* __restrict__ sy, const double* __restrict__ sz,
+                                        const double* __restrict__ sq, const int* __restrict__ st, const int lane,
+                                        const bool diag, const uint32_t m_excl, const uint32_t m_14, const double r2_max,
+                                        double& gix, double& giy, double& giz, double& gjx, double& gjy, double& gjz,
+                                        double& ev, double& ee, unsigned int& n_eval, unsigned int& n_cand) {
+    const int k_begin = (MASKED && diag) ? 1 : 0;
+    const int k_end = (MASKED && diag) ? 17 : 32;
+    const int src = (lane + 1) & 31;
+#pragma unroll 2
+    for (int k = k_begin; k < k_end; ++k) {
+        if (GRAD && k != k_begin) {
+            gjx = __shfl_sync(0xffffffffu, gjx, src);
+            gjy = __shfl_sync(0xffffffffu, gjy, src);
+            gjz = __shfl_sync(0xffffffffu, gjz, src);
+        }
+        const int jj = (lane + k) & 31;
+        const double dx = xi - sx[jj], dy = yi - sy[jj], dz = zi - sz[jj];
+        double r2;
+        if (CUTOFF) {
+            // strict double, left-to-right, no FMA: the r2 the reference's Point3d.distance squares
+            r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        } else {
+            r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+        }
+        double qq2 = qi2 * sq[jj];
+        bool on = true;
+        if (MASKED) {
+            on = !((m_excl >> jj) & 1u);
+            if (diag && k == 16) on = on && (lane < 16);
+            n_cand += __popc(__ballot_sync(0xffffffffu, on));
+            if ((m_14 >> jj) & 1u) qq2 *= kEle14;
+        }
+        if (CUTOFF) {
+            on = on && !(r2 > r2_max);
+            n_eval += __popc(__ballot_sync(0xffffffffu, on));
+        }
+        double e1, e2, f;
+        pair_terms<GRAD>((MASKED || CUTOFF) ? (on ? clamp_r2(r2) : 1.0) : clamp_r2(r2), trow[st[jj]], qq2, e1, e2, f);
+        if (MASKED || CUTOFF) {
+            e1 = on ? e1 : 0.0;
+            e2 = on ? e2 : 0.0;
+            f = on ? f : 0.0;
+        }
+        ev += e1;
+        ee += e2;
+        if (GRAD) {
+            gix = fma(f, dx, gix);
+            giy = fma(f, dy, giy);
+            giz = fma(f, dz, giz);
+            gjx = fma(-f, dx, gjx);
+            gjy = fma(-f, dy, gjy);
+            gjz = fma(-f, dz, gjz);
+        }
+    }
+    if (!MASKED) n_cand += 1024;
+}
+
 template <bool GRAD, bool CUTOFF>
-__global__ void __launch_bounds__(kApThreads, 4)
+__global__ void __launch_bounds__(kApThreads, 5)
 ap_kernel(DeviceSystem S, const ApItem* __restrict__ items, int item_begin, int item_end,
           const int* __restrict__ tile_mask, const TileMask* __restrict__ masks,
           double* __restrict__ gpart, int chunk_slot_base, int tiles_per_item,
@@ -96,7 +168,7 @@ ap_kernel(DeviceSystem S, const ApItem* __restrict__ items, int item_begin, int 
 
     const int ia = it.I * kTile + lane;
     const double xi = S.x[ia], yi = S.y[ia], zi = S.z[ia];
-    const double qi = S.ele_scale * S.q[ia];
+    const double qi2 = 2.0 * S.ele_scale * S.q[ia];         // doubled energies, see pair_terms
     const PairConst* trow = s_table + S.type[ia] * S.n_types;
 
     double gix = 0, giy = 0, giz = 0, ev = 0, ee = 0;
@@ -119,10 +191,11 @@ ap_kernel(DeviceSystem S, const ApItem* __restrict__ items, int item_begin, int 
         sz[lane] = pz;
         sq[lane] = pq;
         st[lane] = pt;
+        const int mi = pm;
         uint32_t m_excl = 0, m_14 = 0;
-        if (pm >= 0) {
-            m_excl = masks[pm].excl[lane];
-            m_14 = masks[pm].f14[lane];
+        if (mi >= 0) {
+            m_excl = masks[mi].excl[lane];
+            m_14 = masks[mi].f14[lane];
         }
         __syncwarp();
         if (t + 1 < it.nd) {
@@ -134,56 +207,16 @@ ap_kernel(DeviceSystem S, const ApItem* __restrict__ items, int item_begin, int 
         }
 
         const bool diag = (d == 0);
-        const int k_begin = diag ? 1 : 0;
-        const int k_end = diag ? 17 : 32;      // diagonal: offsets 1..16, offset 16 only from lanes < 16
         double gjx = 0, gjy = 0, gjz = 0;
-        for (int k = k_begin; k < k_end; ++k) {
-            if (GRAD && k != k_begin) {
-                const int src = (lane + 1) & 31;
-                gjx = shfl_rot1(gjx, src);
-                gjy = shfl_rot1(gjy, src);
-                gjz = shfl_rot1(gjz, src);
-            }
-            const int jj = (lane + k) & 31;
-            const double dx = xi - sx[jj], dy = yi - sy[jj], dz = zi - sz[jj];
-            double r2;
-            if (CUTOFF) {
-                // strict double, left-to-right, no FMA: the r2 the reference's Point3d.distance squares
-                r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-            } else {
-                r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-            }
-            bool on = !((m_excl >> jj) & 1u);
-            if (diag && k == 16) on = on && (lane < 16);
-            n_cand += __popc(__ballot_sync(0xffffffffu, on));
-            if (CUTOFF) {
-                on = on && !(r2 > S.r2_max);
-                n_eval += __popc(__ballot_sync(0xffffffffu, on));
-            }
-            double qq = qi * sq[jj];
-            if ((m_14 >> jj) & 1u) qq *= kEle14;
-            double e1, e2, f;
-            // coincident atoms (r2 == 0, tested on the exponent bits): the buffered energies are finite
-            // there and are kept; the gradient direction is undefined and f * dx = 0 contributes nothing
-            const bool tiny = __double2hiint(r2) < 0x00100000;
-            pair_terms<GRAD>((on && !tiny) ? r2 : (on ? 1e-300 : 1.0), trow[st[jj]], qq, e1, e2, f);
-            e1 = on ? e1 : 0.0;
-            e2 = on ? e2 : 0.0;
-            ev += e1;
-            ee += e2;
-            if (GRAD) {
-                f = on ? f : 0.0;
-                gix = fma(f, dx, gix);
-                giy = fma(f, dy, giy);
-                giz = fma(f, dz, giz);
-                gjx = fma(-f, dx, gjx);
-                gjy = fma(-f, dy, gjy);
-                gjz = fma(-f, dz, gjz);
-            }
-        }
+        if (diag || mi >= 0)
+            ap_tile<GRAD, CUTOFF, true>(xi, yi, zi, qi2, trow, sx, sy, sz, sq, st, lane, diag, m_excl, m_14, S.r2_max,
+                                        gix, giy, giz, gjx, gjy, gjz, ev, ee, n_eval, n_cand);
+        else
+            ap_tile<GRAD, CUTOFF, false>(xi, yi, zi, qi2, trow, sx, sy, sz, sq, st, lane, false, 0u, 0u, S.r2_max,
+                                         gix, giy, giz, gjx, gjy, gjz, ev, ee, n_eval, n_cand);
         if (GRAD) {
             // after the last step the accumulator in lane l belongs to tile atom (l + k_end - 1) & 31
-            const int jo = J * kTile + ((lane + k_end - 1) & 31);
+            const int jo = J * kTile + ((lane + (diag ? 16 : 31)) & 31);
             double* gj = gpart + (size_t)it.I * 3 * S.n_pad;
             gj[jo] = gjx;
             gj[S.n_pad + jo] = gjy;
@@ -197,8 +230,9 @@ ap_kernel(DeviceSystem S, const ApItem* __restrict__ items, int item_begin, int 
         gi[S.n_pad + ia] = giy;
         gi[2 * S.n_pad + ia] = giz;
     }
-    ev = warp_sum(ev);
-    ee = warp_sum(ee);
+    // energies were accumulated doubled (pair_terms)
+    ev = 0.5 * warp_sum(ev);
+    ee = 0.5 * warp_sum(ee);
     if (lane == 0) {
         epart[2 * item_idx] = ev;
         epart[2 * item_idx + 1] = ee;

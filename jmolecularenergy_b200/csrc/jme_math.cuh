@@ -51,57 +51,58 @@ JME_HD double clamp1(double n) { return n > 1 ? 1 : (n < -1 ? -1 : n); }     // 
 //
 // Type-pair constants (precomputed on the host with the reference's operation order, see
 // jme_api.cu build_pair_table):   c2 = 0.07 R*   c3 = 1.12 R*^7   c4 = 0.12 R*^7
-//                                 k1 = eps * (1.07 R*)^7
-// so that  E_vdw = eps (1.07R/(r+0.07R))^7 (1.12R^7/(r^7+0.12R^7) - 2) = k1 s^-7 (c3/t - 2)
+//                                 k1 = 2 eps * (1.07 R*)^7   (doubled, see pair_terms)
+// so that  2 E_vdw = 2 eps (1.07R/(r+0.07R))^7 (1.12R^7/(r^7+0.12R^7) - 2) = k1 s^-7 (c3/t - 2)
 // with s = r + c2, t = r^7 + c4.
 // ---------------------------------------------------------------------------------------------
 struct PairConst {
     double k1, c2, c3, c4;
 };
 
-// r and 1/r from r2 (> 0).  Device: MUFU.RSQ64H seed (about 20 bits) + two coupled Goldschmidt
-// steps -> <= 1 ulp, no slow path.  Host build of this header (tests/hostcheck) uses libm.
-JME_HD void sqrt_and_rsqrt(double r2, double& r, double& rinv) {
+// r and 1/(2r) from r2 (> 0).  Device: MUFU.RSQ64H seed (about 20 bits) + ONE third-order (Halley) step:
+// with e = 1 - r2 y0^2,  1/sqrt(r2) = y0 (1 - e)^(-1/2) = y0 (1 + e/2 + 3e^2/8 + O(e^3)); e ~ 2^-20 leaves a
+// relative error ~ 2^-58, i.e. <= 1 ulp after the final roundings, with no slow path.  The host build of this
+// header (tests/hostcheck) uses libm.
+JME_HD void sqrt_and_half_rsqrt(double r2, double& r, double& half_rinv) {
 #if defined(__CUDA_ARCH__)
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r2));
-    double g = r2 * y;
-    double h = 0.5 * y;
-    double e = fma(-g, h, 0.5);
-    g = fma(g, e, g);
-    h = fma(h, e, h);
-    e = fma(-g, h, 0.5);
-    g = fma(g, e, g);
-    h = fma(h, e, h);
-    r = g;
-    rinv = h + h;
+    const double t = r2 * y;
+    const double e = fma(-t, y, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    const double q = e * p;
+    y = fma(y, q, y);
+    r = r2 * y;
+    half_rinv = 0.5 * y;
 #else
     r = sqrt(r2);
-    rinv = 1.0 / r;
+    half_rinv = 0.5 / r;
 #endif
 }
 
-// 1/x for finite x well inside the normal range.  Device: MUFU.RCP64H seed + two Newton steps.
+// 1/x for finite x well inside the normal range.  Device: MUFU.RCP64H seed + one third-order step:
+// e = 1 - x y0,  1/x = y0 (1 + e + e^2 + O(e^3)).
 JME_HD double fast_rcp(double x) {
 #if defined(__CUDA_ARCH__)
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    return y;
+    const double e = fma(-x, y, 1.0);
+    const double q = fma(e, e, e);
+    return fma(y, q, y);
 #else
     return 1.0 / x;
 #endif
 }
 
-// One pair with r2 > 0.  qq = 332.0716 * qi * qj / D (already x0.75 for a 1-4 pair).
-// Returns e_vdw, e_ele and f_over_r = (dE/dr)/r, so that  dE/dx_i = f_over_r * (x_i - x_j).
+// One pair with r2 > 0.  To save one multiply per pair the kernels work with DOUBLED energies:
+//   pc.k1 = 2 eps (1.07 R*)^7   and   qq2 = 2 * 332.0716 qi qj / D  (x0.75 for a 1-4 pair)
+// so e2_vdw = 2 E_vdw, e2_ele = 2 E_ele, and f_over_r = (dE/dr)/r exactly (the factor 2 cancels against
+// the 1/(2r) the square-root step returns):  dE/dx_i = f_over_r * (x_i - x_j).  Callers halve the energy
+// sums (exact: a power of two).
 template <bool GRAD>
-JME_HD void pair_terms(double r2, const PairConst& pc, double qq, double& e_vdw, double& e_ele, double& f_over_r) {
-    double r, rinv;
-    sqrt_and_rsqrt(r2, r, rinv);
+JME_HD void pair_terms(double r2, const PairConst& pc, double qq2, double& e2_vdw, double& e2_ele, double& f_over_r) {
+    double r, hrinv;
+    sqrt_and_half_rsqrt(r2, r, hrinv);
     const double s = r + pc.c2;
     const double u = r + kEleBuf;
     const double r4 = r2 * r2;
@@ -119,13 +120,13 @@ JME_HD void pair_terms(double r2, const PairConst& pc, double qq, double& e_vdw,
     const double is7 = is4 * is2 * is;
     const double w = pc.k1 * is7;
     const double b = pc.c3 * it;
-    e_vdw = w * (b - 2.0);
-    e_ele = qq * iu;
+    e2_vdw = w * (b - 2.0);
+    e2_ele = qq2 * iu;
     if (GRAD) {
         // dE_vdw/dr = -7 [ E_vdw/s + w b r^6 / t ]      dE_ele/dr = -E_ele/u
-        const double d = fma(w, (b * r6) * it, e_vdw * is);
-        const double g = fma(7.0, d, e_ele * iu);
-        f_over_r = -(g * rinv);
+        const double d = fma(w, (b * r6) * it, e2_vdw * is);
+        const double g = fma(7.0, d, e2_ele * iu);
+        f_over_r = -(g * hrinv);
     } else {
         f_over_r = 0.0;
     }

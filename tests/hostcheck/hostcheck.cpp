@@ -58,11 +58,11 @@ extern "C" int hostcheck_evaluate(const jme_system_t* s, const double* xyz, doub
             double r2 = dx * dx + dy * dy + dz * dz;
             if (cutoff > 0 && r2 > T2) continue;
             ++pairs;
-            double qq = (kEleC * h.charge[i] / dielectric) * h.charge[j];
-            if (cls == 2) qq *= kEle14;
-            double ev, ee, f;
-            pair_terms<true>(r2, h.pair_table[(size_t)h.type_idx[i] * h.n_types + h.type_idx[j]], qq, ev, ee, f);
-            comps[JME_VDW] += ev; comps[JME_ELE] += ee;
+            double qq2 = (2.0 * kEleC * h.charge[i] / dielectric) * h.charge[j];
+            if (cls == 2) qq2 *= kEle14;
+            double ev2, ee2, f;
+            pair_terms<true>(r2, h.pair_table[(size_t)h.type_idx[i] * h.n_types + h.type_idx[j]], qq2, ev2, ee2, f);
+            comps[JME_VDW] += 0.5 * ev2; comps[JME_ELE] += 0.5 * ee2;
             grad[3 * i] += f * dx; grad[3 * i + 1] += f * dy; grad[3 * i + 2] += f * dz;
             grad[3 * j] -= f * dx; grad[3 * j + 1] -= f * dy; grad[3 * j + 2] -= f * dz;
         }
