@@ -57,6 +57,15 @@ def build_system(name: str, scale: float = 1.0):
     raise SystemExit(f"unknown workload {name}")
 
 
+def host_threads() -> int:
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which must not shrink the
+    CPU baseline: the thread count is passed to the oracle explicitly)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -116,7 +125,7 @@ def cpu_baseline(workload: str, faithful: bool, budget_s: float = 20.0):
     work): OpenMP over all threads, type-pair table (`faithful`=False) or the reference's per-pair
     recomputation of R*, eps (`faithful`=True)."""
     from oracle import oracle
-    threads = oracle.num_threads()
+    threads = host_threads()
     cfg = WORKLOADS[workload]
     # size the sample from a quick probe
     scale = {"ions1m": 0.05, "water3k": 1.0, "solvated25k": 1.0}[workload]
@@ -146,7 +155,7 @@ def run_reference(args):
         return
     from oracle import oracle
     cfg = WORKLOADS[args.workload]
-    threads = oracle.num_threads()
+    threads = host_threads()
     scale = {"ions1m": 0.03, "water3k": 1.0, "solvated25k": 0.5}[args.workload]
     s = build_system(args.workload, scale)
     times, pairs = [], 0
@@ -198,6 +207,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
 
