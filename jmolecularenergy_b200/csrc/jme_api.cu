@@ -137,54 +137,55 @@ int fail(jme_handle* h, int code, const std::string& msg) {
 }
 
 // ---- all-pairs plan -------------------------------------------------------------------------
-// Circulant decomposition of the block-pair triangle: row I owns the tiles (I, (I+d) mod nB) for
-// d = 0 .. H(I); every unordered block pair appears exactly once and every row has the same length
-// (+-1), so rows - and ranks owning contiguous item ranges - are balanced.
-inline int half_ring(int nB, int I) {
-    const int full = (nB - 1) / 2;
-    return full + ((nB % 2 == 0 && I < nB / 2) ? 1 : 0);
+// Circulant decomposition over SUPERBLOCKS (kNI 32-atom blocks): row S owns the superblock pairs
+// (S, (S+d) mod nS) for d = 0 .. H(S); every unordered superblock pair appears exactly once and every row has
+// the same length (+-1), so rows - and ranks owning contiguous item ranges - are balanced.  Row S visits the
+// j-tiles q = d*kNI + b (block ((S+d) mod nS)*kNI + b).
+inline int half_ring(int nS, int S) {
+    const int full = (nS - 1) / 2;
+    return full + ((nS % 2 == 0 && S < nS / 2) ? 1 : 0);
 }
 
 int build_allpairs_plan(jme_handle* h) {
     const HostSystem& hs = h->hs;
-    const int nB = h->ds.n_blocks;
+    const int nS = h->ds.n_pad / kSuper;
     const int n = (int)hs.n;
     long long total_tiles = 0;
-    for (int I = 0; I < nB; ++I) total_tiles += half_ring(nB, I) + 1;
+    for (int S = 0; S < nS; ++S) total_tiles += (long long)(half_ring(nS, S) + 1) * kNI;
     if (total_tiles > (1ll << 30)) return fail(h, JME_ERR_UNSUPPORTED, "system too large for the all-pairs path; set a cutoff to use the cell path");
-    // enough items to fill 148 SMs x 16 resident warps a few times over, but >= 1 tile each
-    long long tpi = total_tiles / (148ll * 16 * 4);
+    // enough items to fill 148 SMs x 8 resident warps a few times over, but >= 1 tile each
+    long long tpi = total_tiles / (148ll * 8 * 4);
     tpi = std::max(1ll, std::min(32ll, tpi));
     h->tiles_per_item = (int)tpi;
-    const int max_row = (nB - 1) / 2 + 1 + 1;
+    const int max_row = ((nS - 1) / 2 + 1 + 1) * kNI;
     h->n_chunks = (max_row + (int)tpi - 1) / (int)tpi;
-    h->n_slots = nB + h->n_chunks;
+    h->n_slots = nS + h->n_chunks;
     const size_t gpart_bytes = (size_t)h->n_slots * 3 * h->ds.n_pad * sizeof(double);
     if (gpart_bytes > (size_t)96 << 30) return fail(h, JME_ERR_UNSUPPORTED, "all-pairs partial-gradient buffer would exceed 96 GiB; set a cutoff to use the cell path");
 
     h->items.clear();
-    std::vector<int> row_first_item(nB + 1, 0);
+    std::vector<int> row_first_item(nS + 1, 0);
     int tile_ofs = 0;
-    for (int I = 0; I < nB; ++I) {
-        row_first_item[I] = (int)h->items.size();
-        const int len = half_ring(nB, I) + 1;
-        for (int d0 = 0; d0 < len; d0 += (int)tpi) {
-            ApItem it{I, d0, std::min((int)tpi, len - d0), tile_ofs};
-            tile_ofs += it.nd;
+    for (int S = 0; S < nS; ++S) {
+        row_first_item[S] = (int)h->items.size();
+        const int len = (half_ring(nS, S) + 1) * kNI;
+        for (int q0 = 0; q0 < len; q0 += (int)tpi) {
+            ApItem it{S, q0, std::min((int)tpi, len - q0), tile_ofs};
+            tile_ofs += it.nq;
             h->items.push_back(it);
         }
     }
-    row_first_item[nB] = (int)h->items.size();
+    row_first_item[nS] = (int)h->items.size();
 
     // tile masks
     std::vector<int> tile_mask((size_t)total_tiles, -1);
     std::vector<TileMask> masks;
-    auto tile_index = [&](int I, int d) {
-        const ApItem& it = h->items[row_first_item[I] + d / (int)tpi];
-        return it.tile_ofs + (d - it.d0);
+    auto tile_index = [&](int S, int q) {
+        const ApItem& it = h->items[row_first_item[S] + q / (int)tpi];
+        return it.tile_ofs + (q - it.q0);
     };
-    auto mask_of = [&](int I, int d) -> TileMask& {
-        int& m = tile_mask[tile_index(I, d)];
+    auto mask_of = [&](int S, int q) -> TileMask& {
+        int& m = tile_mask[tile_index(S, q)];
         if (m < 0) {
             m = (int)masks.size();
             masks.emplace_back();
@@ -192,10 +193,10 @@ int build_allpairs_plan(jme_handle* h) {
         }
         return masks[m];
     };
-    // which row owns the block pair {A, B}, and at which offset
-    auto owner = [&](int A, int B, int& I, int& d) {
-        const int d1 = (B - A + nB) % nB, d2 = nB - d1;
-        if (d1 < d2 || (d1 == d2 && A < B)) { I = A; d = d1; } else { I = B; d = d2; }
+    // which row owns the superblock pair {A, B}, and at which offset
+    auto owner = [&](int A, int B, int& S, int& d) {
+        const int d1 = (B - A + nS) % nS, d2 = nS - d1;
+        if (d1 < d2 || (d1 == d2 && A < B)) { S = A; d = d1; } else { S = B; d = d2; }
     };
     for (int64_t i = 0; i < n; ++i)
         for (int64_t e = hs.excl_ptr[i]; e < hs.excl_ptr[i + 1]; ++e) {
@@ -204,32 +205,40 @@ int build_allpairs_plan(jme_handle* h) {
             if (j <= i) continue;
             const bool is14 = (v & kFlag14) != 0;
             const int A = (int)(i / kTile), B = (int)(j / kTile), li = (int)(i % kTile), lj = (int)(j % kTile);
-            if (A == B) {
-                TileMask& m = mask_of(A, 0);
-                // the diagonal tile visits an unordered pair from one of its two lanes: mark both
-                if (is14) { m.f14[li] |= 1u << lj; m.f14[lj] |= 1u << li; }
-                else { m.excl[li] |= 1u << lj; m.excl[lj] |= 1u << li; }
+            const int SA = A / kNI, SB = B / kNI;
+            int S, q, chain, row, bit;
+            if (SA == SB) {
+                // inside one superblock the pair is met by chain A%kNI (the lower block) on tile B%kNI;
+                // on the diagonal tile (A == B) the kernel keeps j > i, i.e. lane li meets bit lj
+                S = SA; q = B % kNI; chain = A % kNI; row = li; bit = lj;
             } else {
-                int I, d;
-                owner(A, B, I, d);
-                TileMask& m = mask_of(I, d);
-                const int row = (I == A) ? li : lj, bit = (I == A) ? lj : li;
-                if (is14) m.f14[row] |= 1u << bit; else m.excl[row] |= 1u << bit;
+                int d;
+                owner(SA, SB, S, d);
+                if (S == SA) { q = d * kNI + B % kNI; chain = A % kNI; row = li; bit = lj; }
+                else { q = d * kNI + A % kNI; chain = B % kNI; row = lj; bit = li; }
             }
+            TileMask& m = mask_of(S, q);
+            if (is14) m.f14[chain][row] |= 1u << bit; else m.excl[chain][row] |= 1u << bit;
         }
     if (h->ds.n_pad > n) {
-        // padding atoms of the last block never interact
-        const int L = nB - 1, valid = n - L * kTile;
-        const uint32_t pad_bits = valid >= 32 ? 0u : (0xffffffffu << valid);
-        for (int I = 0; I < nB; ++I) {
-            const int len = half_ring(nB, I) + 1;
-            for (int d = 0; d < len; ++d) {
-                const int J = (I + d) % nB;
-                if (I != L && J != L) continue;
-                TileMask& m = mask_of(I, d);
-                for (int r = 0; r < 32; ++r) {
-                    if (I == L && r >= valid) m.excl[r] = 0xffffffffu;
-                    if (J == L) m.excl[r] |= pad_bits;
+        // padding atoms (index >= n) never interact
+        auto valid_in_block = [&](int B) { return std::max(0, std::min(kTile, n - B * kTile)); };
+        const int first_pad_block = n / kTile;
+        for (int S = 0; S < nS; ++S) {
+            const int len = (half_ring(nS, S) + 1) * kNI;
+            const bool i_has_pad = (S * kNI + kNI - 1) >= first_pad_block;
+            for (int q = 0; q < len; ++q) {
+                const int J = ((S + q / kNI) % nS) * kNI + q % kNI;
+                if (!i_has_pad && J < first_pad_block) continue;
+                TileMask& m = mask_of(S, q);
+                const int vj = valid_in_block(J);
+                const uint32_t pad_bits = vj >= 32 ? 0u : (0xffffffffu << vj);
+                for (int a = 0; a < kNI; ++a) {
+                    const int vi = valid_in_block(S * kNI + a);
+                    for (int r = 0; r < 32; ++r) {
+                        if (r >= vi) m.excl[a][r] = 0xffffffffu;
+                        m.excl[a][r] |= pad_bits;
+                    }
                 }
             }
         }
@@ -338,22 +347,31 @@ cudaEvent_t* prof_slot(jme_handle* h) {
 }
 
 size_t ap_smem_bytes(const DeviceSystem& ds) {
-    return (size_t)ds.n_types * ds.n_types * sizeof(PairConst) + kApWarps * (4 * 32 + 16) * sizeof(double);
+    return (size_t)ds.n_types * ds.n_types * sizeof(PairConst) + kApWarps * (4 * 32 + 16) * sizeof(double) +
+           kApWarps * (kNI * 3 + 3) * 32 * sizeof(double);
 }
 
-template <bool GRAD, bool CUTOFF>
-int launch_ap(jme_handle* h) {
+template <bool GRAD, bool CUTOFF, int KSPLIT>
+int launch_ap_k(jme_handle* h) {
     const int n_items = h->item_end - h->item_begin;
     if (n_items <= 0) return JME_OK;
     const size_t smem = ap_smem_bytes(h->ds);
-    auto kern = ap_kernel<GRAD, CUTOFF>;
+    auto kern = ap_kernel<GRAD, CUTOFF, KSPLIT>;
     if (smem > 48 * 1024) JME_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = (n_items + kApWarps - 1) / kApWarps;
+    const int grid = KSPLIT == 1 ? (n_items + kApWarps - 1) / kApWarps : n_items;
     kern<<<grid, kApThreads, smem, h->stream>>>(h->ds, h->d_items, h->item_begin, h->item_end, h->d_tile_mask, h->d_masks,
-                                                h->d_gpart, h->ds.n_blocks, h->tiles_per_item, h->d_epart, h->d_cpart);
+                                                h->ds.n_pad / kSuper, h->d_gpart, h->tiles_per_item, h->d_epart, h->d_cpart);
     ++h->launches;
     JME_CUDA(h, cudaGetLastError());
     return JME_OK;
+}
+
+// Small systems do not have enough tiles to fill the chip with one warp per item: let the four warps of a CTA
+// share an item (a quarter of each tile's steps each).
+template <bool GRAD, bool CUTOFF>
+int launch_ap(jme_handle* h) {
+    const long long n_items = h->item_end - h->item_begin;
+    return n_items < 148ll * 8 * 3 ? launch_ap_k<GRAD, CUTOFF, kApWarps>(h) : launch_ap_k<GRAD, CUTOFF, 1>(h);
 }
 
 // Enqueue one evaluation; results land in h->d_out (or d_out_user).
@@ -445,7 +463,7 @@ int jme_create(const jme_system_t* sys, jme_handle_t** out) {
 
     const HostSystem& hs = h->hs;
     const int n = (int)hs.n;
-    const int n_pad = std::max(kTile, (n + kTile - 1) / kTile * kTile);
+    const int n_pad = std::max(kSuper, (n + kSuper - 1) / kSuper * kSuper);
     int rc;
     auto alloc_zero = [&](double** p, size_t cnt) -> int {
         int r = dev_alloc(h, p, cnt);
@@ -648,9 +666,9 @@ int jme_pair_list(jme_handle_t* h, int32_t* pair_i, int32_t* pair_j, uint8_t* is
         if (n_items > 0) {
             const int grid = (n_items + kApWarps - 1) / kApWarps;
             if (h->cutoff > 0)
-                ap_pairlist_kernel<true><<<grid, kApThreads, 0, h->stream>>>(h->ds, h->d_items, h->item_begin, h->item_end, h->d_tile_mask, h->d_masks, d_i, d_j, d_f, capacity, d_cur);
+                ap_pairlist_kernel<true><<<grid, kApThreads, 0, h->stream>>>(h->ds, h->d_items, h->item_begin, h->item_end, h->d_tile_mask, h->d_masks, h->ds.n_pad / kSuper, d_i, d_j, d_f, capacity, d_cur);
             else
-                ap_pairlist_kernel<false><<<grid, kApThreads, 0, h->stream>>>(h->ds, h->d_items, h->item_begin, h->item_end, h->d_tile_mask, h->d_masks, d_i, d_j, d_f, capacity, d_cur);
+                ap_pairlist_kernel<false><<<grid, kApThreads, 0, h->stream>>>(h->ds, h->d_items, h->item_begin, h->item_end, h->d_tile_mask, h->d_masks, h->ds.n_pad / kSuper, d_i, d_j, d_f, capacity, d_cur);
             ++h->launches;
         }
     } else {

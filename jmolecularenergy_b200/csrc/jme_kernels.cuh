@@ -22,15 +22,15 @@
 namespace jme {
 
 constexpr int kTile = 32;
-constexpr int kApWarps = 4;                    // warps per CTA in ap_kernel
+constexpr int kApWarps = 4;                    // warps per CTA in ap_kernel (2 CTAs/SM: 2 warps per scheduler)
 constexpr int kApThreads = kApWarps * 32;
 constexpr int kReduceWarps = 8;
 constexpr int kBondedThreads = 128;
 
 struct DeviceSystem {
     int n;                 // atoms
-    int n_pad;             // padded to a multiple of 32
-    int n_blocks;          // n_pad / 32
+    int n_pad;             // padded to a multiple of 128 (kSuper)
+    int n_blocks;          // n_pad / 32 (n_pad is a multiple of 128: whole superblocks)
     int n_types;
     const double* x;       // [n_pad] SoA coordinates (padding = 0)
     const double* y;
@@ -42,15 +42,27 @@ struct DeviceSystem {
     double ele_scale;      // 332.0716 / dielectric
 };
 
-// One work item of the all-pairs path: i-block I against j-blocks J = (I + d) mod n_blocks for
-// d in [d0, d0 + nd).  d = 0 is the diagonal tile.  tile_ofs indexes tile_mask[].
+// ---- all-pairs decomposition ---------------------------------------------------------------------
+// Atoms are grouped in 32-atom blocks and kNI consecutive blocks form a SUPERBLOCK.  A warp owns one
+// superblock S as its i-side: lane l holds the kNI atoms  (S*kNI + a)*32 + l,  a = 0..kNI-1  ("chains").
+// It meets 32-atom j-tiles one after the other; every j atom is loaded once per step and paired with all
+// kNI i atoms of the lane - kNI independent FP64 dependency chains per lane, which is what the FP64 pipe
+// needs (measured on B200, tools/fp64_latency.cu: 8.3 cycles dependent latency; 2.25 cycles per warp
+// instruction with >= 4 chains in ONE warp, but 3.1 when the same parallelism comes from 8 warps).
+// The j-tile sequence of row S is  q = 0 .. (H(S)+1)*kNI - 1 :  d = q / kNI, b = q % kNI,
+// j-block = ((S + d) mod nS)*kNI + b  (circulant over superblocks: every superblock pair exactly once);
+// d = 0 is the superblock against itself, where chain a meets tile b only if a <= b and the tile a == b
+// keeps only j > i.
+constexpr int kNI = 4;
+constexpr int kSuper = kNI * kTile;          // atoms per superblock (128)
+
 struct ApItem {
-    int I, d0, nd, tile_ofs;
+    int S, q0, nq, tile_ofs;                 // tiles q0 .. q0+nq-1 of row S; tile_ofs indexes tile_mask[]
 };
 
 struct TileMask {
-    uint32_t excl[32];     // row = i-lane, bit = j index in the tile: pair excluded (1-2, 1-3, padding)
-    uint32_t f14[32];      // pair is a 1-4 pair (electrostatics x0.75)
+    uint32_t excl[kNI][32];     // [chain][i-lane], bit = j index in the tile: excluded (1-2, 1-3, padding)
+    uint32_t f14[kNI][32];      // 1-4 pair (electrostatics x0.75)
 };
 
 __device__ __forceinline__ double shfl_rot1(double v, int src_lane) {
@@ -66,33 +78,38 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ---------------------------------------------------------------------------------------------
 // all-pairs tiles
 // ---------------------------------------------------------------------------------------------
-// gpart layout: [slot][3][n_pad].  Slot I (< n_blocks) receives the j-side gradients produced by the
-// items of i-block I; slot n_blocks + c receives the i-side gradients of chunk c of every row.  Each
+// gpart layout: [slot][3][n_pad].  Slot S (< n_super) receives the j-side gradients produced by the items of
+// superblock row S; slot n_super + c receives the i-side gradients of chunk c of every row.  Each
 // (slot, atom) has exactly one writer, so the later fixed-order sum is deterministic.
+
 // r2 with its exponent clamped from below (integer max on the high word): coincident atoms (r2 == 0) keep
 // their finite buffered energy and get no gradient (f * dx = 0), without a NaN from 1/sqrt(0)
 __device__ __forceinline__ double clamp_r2(double r2) {
     return __hiloint2double(max(__double2hiint(r2), 0x01a00000), __double2loint(r2));
 }
 
-// One 32x32 tile.  Lane l owns i-atom l of the row block; at step k it meets j-atom (l + k) & 31 of the
-// staged tile, so every step touches 32 distinct j atoms and the j-side accumulator that travels with
-// atom (l + k) is handed from lane l+1 to lane l between steps (warp shuffle).
-//   MASKED = false : plain off-diagonal tile, all 1024 pairs interact - no predicate, no selects
-//   MASKED = true  : diagonal tile (offsets 1..16, offset 16 from lanes < 16 only) and/or exclusion,
-//                    1-4 and padding bit masks
+struct ApLaneState {            // the kNI i-atoms of a lane
+    double xi[kNI], yi[kNI], zi[kNI], qi2[kNI];
+    double gix[kNI], giy[kNI], giz[kNI];
+    const PairConst* trow[kNI];
+};
+
+// One 32-atom j-tile against the kNI i-chains of every lane.  At step k lane l meets j-atom (l + k) & 31;
+// the j-side accumulator travels with the j atom from lane l+1 to lane l between steps (warp shuffle), so
+// Newton's third law costs no atomics and no scatter.
+//   MASKED = false : every pair of the tile interacts with every chain - no predicates, no selects
+//   MASKED = true  : per chain: active flag, "self" rule (tile == own block: only j > i), exclusion / 1-4 /
+//                    padding bit masks
 template <bool GRAD, bool CUTOFF, bool MASKED>
-__device__ __forceinline__ void ap_tile(const double xi, const double yi, const double zi, const double qi2,
-                                        const PairConst* __restrict__ trow, const double* __restrict__ sx,
-                                        const double* __restrict__ sy, const double* __restrict__ sz,
-                                        const double* __restrict__ sq, const int* __restrict__ st, const int lane,
-                                        const bool diag, const uint32_t m_excl, const uint32_t m_14, const double r2_max,
-                                        double& gix, double& giy, double& giz, double& gjx, double& gjy, double& gjz,
+__device__ __forceinline__ void ap_tile(ApLaneState& L, const double* __restrict__ sx, const double* __restrict__ sy,
+                                        const double* __restrict__ sz, const double* __restrict__ sq,
+                                        const int* __restrict__ st, const int lane, const int k_begin, const int k_end,
+                                        const int active_chains,
+                                        const int self_chain, const uint32_t (&m_excl)[kNI], const uint32_t (&m_14)[kNI],
+                                        const double r2_max, double& gjx, double& gjy, double& gjz,
                                         double& ev, double& ee, unsigned int& n_eval, unsigned int& n_cand) {
-    const int k_begin = (MASKED && diag) ? 1 : 0;
-    const int k_end = (MASKED && diag) ? 17 : 32;
     const int src = (lane + 1) & 31;
-#pragma unroll 2
+#pragma unroll 1
     for (int k = k_begin; k < k_end; ++k) {
         if (GRAD && k != k_begin) {
             gjx = __shfl_sync(0xffffffffu, gjx, src);
@@ -100,58 +117,69 @@ __device__ __forceinline__ void ap_tile(const double xi, const double yi, const 
             gjz = __shfl_sync(0xffffffffu, gjz, src);
         }
         const int jj = (lane + k) & 31;
-        const double dx = xi - sx[jj], dy = yi - sy[jj], dz = zi - sz[jj];
-        double r2;
-        if (CUTOFF) {
-            // strict double, left-to-right, no FMA: the r2 the reference's Point3d.distance squares
-            r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-        } else {
-            r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-        }
-        double qq2 = qi2 * sq[jj];
-        bool on = true;
-        if (MASKED) {
-            on = !((m_excl >> jj) & 1u);
-            if (diag && k == 16) on = on && (lane < 16);
-            n_cand += __popc(__ballot_sync(0xffffffffu, on));
-            if ((m_14 >> jj) & 1u) qq2 *= kEle14;
-        }
-        if (CUTOFF) {
-            on = on && !(r2 > r2_max);
-            n_eval += __popc(__ballot_sync(0xffffffffu, on));
-        }
-        double e1, e2, f;
-        pair_terms<GRAD>((MASKED || CUTOFF) ? (on ? clamp_r2(r2) : 1.0) : clamp_r2(r2), trow[st[jj]], qq2, e1, e2, f);
-        if (MASKED || CUTOFF) {
-            e1 = on ? e1 : 0.0;
-            e2 = on ? e2 : 0.0;
-            f = on ? f : 0.0;
-        }
-        ev += e1;
-        ee += e2;
-        if (GRAD) {
-            gix = fma(f, dx, gix);
-            giy = fma(f, dy, giy);
-            giz = fma(f, dz, giz);
-            gjx = fma(-f, dx, gjx);
-            gjy = fma(-f, dy, gjy);
-            gjz = fma(-f, dz, gjz);
+        const double xj = sx[jj], yj = sy[jj], zj = sz[jj], qj = sq[jj];
+        const int tj = st[jj];
+#pragma unroll
+        for (int a = 0; a < kNI; ++a) {
+            const double dx = L.xi[a] - xj, dy = L.yi[a] - yj, dz = L.zi[a] - zj;
+            double r2;
+            if (CUTOFF) {
+                // strict double, left-to-right, no FMA: the r2 the reference's Point3d.distance squares
+                r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            } else {
+                r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            }
+            double qq2 = L.qi2[a] * qj;
+            bool on = true;
+            if (MASKED) {
+                on = (a < active_chains) && !((m_excl[a] >> jj) & 1u);
+                if (a == self_chain) on = on && (jj > lane);
+                n_cand += __popc(__ballot_sync(0xffffffffu, on));
+                if ((m_14[a] >> jj) & 1u) qq2 *= kEle14;
+            }
+            if (CUTOFF) {
+                on = on && !(r2 > r2_max);
+                n_eval += __popc(__ballot_sync(0xffffffffu, on));
+            }
+            double e1, e2, f;
+            pair_terms<GRAD>((MASKED || CUTOFF) ? (on ? clamp_r2(r2) : 1.0) : clamp_r2(r2), L.trow[a][tj], qq2, e1, e2, f);
+            if (MASKED || CUTOFF) {
+                e1 = on ? e1 : 0.0;
+                e2 = on ? e2 : 0.0;
+                f = on ? f : 0.0;
+            }
+            ev += e1;
+            ee += e2;
+            if (GRAD) {
+                L.gix[a] = fma(f, dx, L.gix[a]);
+                L.giy[a] = fma(f, dy, L.giy[a]);
+                L.giz[a] = fma(f, dz, L.giz[a]);
+                gjx = fma(-f, dx, gjx);
+                gjy = fma(-f, dy, gjy);
+                gjz = fma(-f, dz, gjz);
+            }
         }
     }
-    if (!MASKED) n_cand += 1024;
+    if (!MASKED) n_cand += 32 * (k_end - k_begin) * kNI;
 }
 
-template <bool GRAD, bool CUTOFF>
-__global__ void __launch_bounds__(kApThreads, 5)
+// KSPLIT = 1: every warp of the CTA works on its own item (large systems: plenty of items).
+// KSPLIT = 4: the four warps of the CTA share ONE item and each takes a quarter of the 32 steps of every tile
+//             (small systems: 4x more parallelism per tile); the partial sums of the four warps are combined in
+//             shared memory in a fixed order, so the outputs are the same buffers as for KSPLIT = 1.
+template <bool GRAD, bool CUTOFF, int KSPLIT>
+__global__ void __launch_bounds__(kApThreads, 2)
 ap_kernel(DeviceSystem S, const ApItem* __restrict__ items, int item_begin, int item_end,
-          const int* __restrict__ tile_mask, const TileMask* __restrict__ masks,
-          double* __restrict__ gpart, int chunk_slot_base, int tiles_per_item,
+          const int* __restrict__ tile_mask, const TileMask* __restrict__ masks, int n_super,
+          double* __restrict__ gpart, int tiles_per_item,
           double* __restrict__ epart, unsigned long long* __restrict__ cpart) {
+    static_assert(KSPLIT == 1 || KSPLIT == kApWarps, "KSPLIT must be 1 or the number of warps per CTA");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // shared: pair table, then per-warp j staging (x, y, z, q: 4 x 32 doubles; type: 32 ints)
+    // shared: pair table, per-warp j staging (x, y, z, q: 4 x 32 doubles; type: 32 ints), KSPLIT combine area
     PairConst* s_table = reinterpret_cast<PairConst*>(smem_raw);
     const int TT = S.n_types * S.n_types;
     double* s_stage = reinterpret_cast<double*>(s_table + TT);
+    double* s_comb = s_stage + kApWarps * (4 * 32 + 16);       // [warps][kNI*3 + 3][32] (KSPLIT > 1 only)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* sx = s_stage + warp * (4 * 32 + 16);
     double* sy = sx + 32;
@@ -162,28 +190,38 @@ ap_kernel(DeviceSystem S, const ApItem* __restrict__ items, int item_begin, int 
     for (int t = threadIdx.x; t < TT; t += kApThreads) s_table[t] = S.table[t];
     __syncthreads();
 
-    const int item_idx = item_begin + blockIdx.x * kApWarps + warp;
-    if (item_idx >= item_end) return;
+    const int item_idx = item_begin + (KSPLIT == 1 ? blockIdx.x * kApWarps + warp : (int)blockIdx.x);
+    if (item_idx >= item_end) return;           // CTA-uniform when KSPLIT > 1
     const ApItem it = items[item_idx];
+    const int k_begin = KSPLIT == 1 ? 0 : warp * (32 / kApWarps);
+    const int k_end = KSPLIT == 1 ? 32 : k_begin + 32 / kApWarps;
 
-    const int ia = it.I * kTile + lane;
-    const double xi = S.x[ia], yi = S.y[ia], zi = S.z[ia];
-    const double qi2 = 2.0 * S.ele_scale * S.q[ia];         // doubled energies, see pair_terms
-    const PairConst* trow = s_table + S.type[ia] * S.n_types;
-
-    double gix = 0, giy = 0, giz = 0, ev = 0, ee = 0;
+    ApLaneState L;
+#pragma unroll
+    for (int a = 0; a < kNI; ++a) {
+        const int ia = (it.S * kNI + a) * kTile + lane;
+        L.xi[a] = S.x[ia]; L.yi[a] = S.y[ia]; L.zi[a] = S.z[ia];
+        L.qi2[a] = 2.0 * S.ele_scale * S.q[ia];             // doubled energies, see pair_terms
+        L.trow[a] = s_table + S.type[ia] * S.n_types;
+        L.gix[a] = L.giy[a] = L.giz[a] = 0.0;
+    }
+    double ev = 0, ee = 0;
     unsigned int n_eval = 0, n_cand = 0;
 
+    auto j_block = [&](int q) {
+        int T = it.S + q / kNI;
+        if (T >= n_super) T -= n_super;
+        return T * kNI + q % kNI;
+    };
     // software pipeline: the next tile's atoms are loaded into registers while this tile computes
-    int Jn = it.I + it.d0;
-    if (Jn >= S.n_blocks) Jn -= S.n_blocks;
+    int Jn = j_block(it.q0);
     double px = S.x[Jn * kTile + lane], py = S.y[Jn * kTile + lane], pz = S.z[Jn * kTile + lane];
     double pq = S.q[Jn * kTile + lane];
     int pt = S.type[Jn * kTile + lane];
     int pm = tile_mask[it.tile_ofs];
 
-    for (int t = 0; t < it.nd; ++t) {
-        const int d = it.d0 + t;
+    for (int t = 0; t < it.nq; ++t) {
+        const int q = it.q0 + t;
         const int J = Jn;
         __syncwarp();
         sx[lane] = px;
@@ -192,53 +230,126 @@ ap_kernel(DeviceSystem S, const ApItem* __restrict__ items, int item_begin, int 
         sq[lane] = pq;
         st[lane] = pt;
         const int mi = pm;
-        uint32_t m_excl = 0, m_14 = 0;
-        if (mi >= 0) {
-            m_excl = masks[mi].excl[lane];
-            m_14 = masks[mi].f14[lane];
-        }
         __syncwarp();
-        if (t + 1 < it.nd) {
-            Jn = it.I + d + 1;
-            if (Jn >= S.n_blocks) Jn -= S.n_blocks;
+        if (t + 1 < it.nq) {
+            Jn = j_block(q + 1);
             const int na = Jn * kTile + lane;
             px = S.x[na]; py = S.y[na]; pz = S.z[na]; pq = S.q[na]; pt = S.type[na];
             pm = tile_mask[it.tile_ofs + t + 1];
         }
 
-        const bool diag = (d == 0);
+        const bool self = q < kNI;                 // d == 0: the superblock against itself
         double gjx = 0, gjy = 0, gjz = 0;
-        if (diag || mi >= 0)
-            ap_tile<GRAD, CUTOFF, true>(xi, yi, zi, qi2, trow, sx, sy, sz, sq, st, lane, diag, m_excl, m_14, S.r2_max,
-                                        gix, giy, giz, gjx, gjy, gjz, ev, ee, n_eval, n_cand);
-        else
-            ap_tile<GRAD, CUTOFF, false>(xi, yi, zi, qi2, trow, sx, sy, sz, sq, st, lane, false, 0u, 0u, S.r2_max,
-                                         gix, giy, giz, gjx, gjy, gjz, ev, ee, n_eval, n_cand);
+        if (self || mi >= 0) {
+            uint32_t m_excl[kNI], m_14[kNI];
+#pragma unroll
+            for (int a = 0; a < kNI; ++a) {
+                m_excl[a] = mi >= 0 ? masks[mi].excl[a][lane] : 0u;
+                m_14[a] = mi >= 0 ? masks[mi].f14[a][lane] : 0u;
+            }
+            // self tiles: tile b = q meets chains a <= b only, chain a == b keeps j > i
+            ap_tile<GRAD, CUTOFF, true>(L, sx, sy, sz, sq, st, lane, k_begin, k_end, self ? q + 1 : kNI, self ? q : -1,
+                                        m_excl, m_14, S.r2_max, gjx, gjy, gjz, ev, ee, n_eval, n_cand);
+        } else {
+            const uint32_t zero[kNI] = {};
+            ap_tile<GRAD, CUTOFF, false>(L, sx, sy, sz, sq, st, lane, k_begin, k_end, kNI, -1, zero, zero, S.r2_max,
+                                         gjx, gjy, gjz, ev, ee, n_eval, n_cand);
+        }
         if (GRAD) {
-            // after the last step the accumulator in lane l belongs to tile atom (l + k_end - 1) & 31
-            const int jo = J * kTile + ((lane + (diag ? 16 : 31)) & 31);
-            double* gj = gpart + (size_t)it.I * 3 * S.n_pad;
-            gj[jo] = gjx;
-            gj[S.n_pad + jo] = gjy;
-            gj[2 * S.n_pad + jo] = gjz;
+            // after its last step the accumulator in lane l belongs to tile atom (l + k_end - 1) & 31
+            const int jl = (lane + k_end - 1) & 31;
+            double* gj = gpart + (size_t)it.S * 3 * S.n_pad + J * kTile;
+            if (KSPLIT == 1) {
+                gj[jl] = gjx;
+                gj[S.n_pad + jl] = gjy;
+                gj[2 * S.n_pad + jl] = gjz;
+            } else {
+                double* c = s_comb + warp * ((kNI * 3 + 3) * 32);
+                __syncthreads();                    // previous tile's combine has been consumed
+                c[jl] = gjx; c[32 + jl] = gjy; c[64 + jl] = gjz;
+                __syncthreads();
+                if (warp == 0) {
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc) {
+                        double v = 0;
+#pragma unroll
+                        for (int w = 0; w < kApWarps; ++w) v += s_comb[w * ((kNI * 3 + 3) * 32) + cc * 32 + lane];
+                        gj[cc * (size_t)S.n_pad + lane] = v;
+                    }
+                }
+            }
         }
     }
-    if (GRAD) {
-        const int chunk = it.d0 / tiles_per_item;
-        double* gi = gpart + (size_t)(chunk_slot_base + chunk) * 3 * S.n_pad;
-        gi[ia] = gix;
-        gi[S.n_pad + ia] = giy;
-        gi[2 * S.n_pad + ia] = giz;
-    }
-    // energies were accumulated doubled (pair_terms)
-    ev = 0.5 * warp_sum(ev);
-    ee = 0.5 * warp_sum(ee);
-    if (lane == 0) {
-        epart[2 * item_idx] = ev;
-        epart[2 * item_idx + 1] = ee;
-        // ballots are warp-uniform: every lane holds the same counts
-        cpart[2 * item_idx] = CUTOFF ? n_eval : n_cand;
-        cpart[2 * item_idx + 1] = n_cand;
+    ev = warp_sum(ev);
+    ee = warp_sum(ee);
+    if (KSPLIT == 1) {
+        if (GRAD) {
+            const int chunk = it.q0 / tiles_per_item;
+            double* gi = gpart + (size_t)(n_super + chunk) * 3 * S.n_pad;
+#pragma unroll
+            for (int a = 0; a < kNI; ++a) {
+                const int ia = (it.S * kNI + a) * kTile + lane;
+                gi[ia] = L.gix[a];
+                gi[S.n_pad + ia] = L.giy[a];
+                gi[2 * S.n_pad + ia] = L.giz[a];
+            }
+        }
+        if (lane == 0) {
+            // energies were accumulated doubled (pair_terms); ballots are warp-uniform: every lane holds the counts
+            epart[2 * item_idx] = 0.5 * ev;
+            epart[2 * item_idx + 1] = 0.5 * ee;
+            cpart[2 * item_idx] = CUTOFF ? n_eval : n_cand;
+            cpart[2 * item_idx + 1] = n_cand;
+        }
+    } else {
+        double* c = s_comb + warp * ((kNI * 3 + 3) * 32);
+        __syncthreads();
+        if (GRAD) {
+#pragma unroll
+            for (int a = 0; a < kNI; ++a) {
+                c[(3 * a) * 32 + lane] = L.gix[a];
+                c[(3 * a + 1) * 32 + lane] = L.giy[a];
+                c[(3 * a + 2) * 32 + lane] = L.giz[a];
+            }
+        }
+        if (lane == 0) {
+            c[kNI * 3 * 32] = ev;
+            c[kNI * 3 * 32 + 1] = ee;
+            c[kNI * 3 * 32 + 2] = (double)(CUTOFF ? n_eval : n_cand);
+            c[kNI * 3 * 32 + 3] = (double)n_cand;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const int stride = (kNI * 3 + 3) * 32;
+            if (GRAD) {
+                const int chunk = it.q0 / tiles_per_item;
+                double* gi = gpart + (size_t)(n_super + chunk) * 3 * S.n_pad;
+#pragma unroll
+                for (int a = 0; a < kNI; ++a) {
+                    const int ia = (it.S * kNI + a) * kTile + lane;
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc) {
+                        double v = 0;
+#pragma unroll
+                        for (int w = 0; w < kApWarps; ++w) v += s_comb[w * stride + (3 * a + cc) * 32 + lane];
+                        gi[cc * (size_t)S.n_pad + ia] = v;
+                    }
+                }
+            }
+            if (lane == 0) {
+                double e0 = 0, e1 = 0, c0 = 0, c1 = 0;
+                for (int w = 0; w < kApWarps; ++w) {
+                    e0 += s_comb[w * stride + kNI * 3 * 32];
+                    e1 += s_comb[w * stride + kNI * 3 * 32 + 1];
+                    c0 += s_comb[w * stride + kNI * 3 * 32 + 2];
+                    c1 += s_comb[w * stride + kNI * 3 * 32 + 3];
+                }
+                epart[2 * item_idx] = 0.5 * e0;
+                epart[2 * item_idx + 1] = 0.5 * e1;
+                cpart[2 * item_idx] = (unsigned long long)c0;
+                cpart[2 * item_idx + 1] = (unsigned long long)c1;
+            }
+        }
     }
 }
 
@@ -247,41 +358,41 @@ ap_kernel(DeviceSystem S, const ApItem* __restrict__ items, int item_begin, int 
 template <bool CUTOFF>
 __global__ void __launch_bounds__(kApThreads)
 ap_pairlist_kernel(DeviceSystem S, const ApItem* __restrict__ items, int item_begin, int item_end,
-                   const int* __restrict__ tile_mask, const TileMask* __restrict__ masks,
+                   const int* __restrict__ tile_mask, const TileMask* __restrict__ masks, int n_super,
                    int* __restrict__ out_i, int* __restrict__ out_j, unsigned char* __restrict__ out_14,
                    long long capacity, unsigned long long* __restrict__ cursor) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item_idx = item_begin + blockIdx.x * kApWarps + warp;
     if (item_idx >= item_end) return;
     const ApItem it = items[item_idx];
-    const int ia = it.I * kTile + lane;
-    const double xi = S.x[ia], yi = S.y[ia], zi = S.z[ia];
-    for (int t = 0; t < it.nd; ++t) {
-        const int d = it.d0 + t;
-        int J = it.I + d;
-        if (J >= S.n_blocks) J -= S.n_blocks;
-        uint32_t m_excl = 0, m_14 = 0;
+    for (int t = 0; t < it.nq; ++t) {
+        const int q = it.q0 + t;
+        int T = it.S + q / kNI;
+        if (T >= n_super) T -= n_super;
+        const int J = T * kNI + q % kNI;
         const int mi = tile_mask[it.tile_ofs + t];
-        if (mi >= 0) {
-            m_excl = masks[mi].excl[lane];
-            m_14 = masks[mi].f14[lane];
-        }
-        const bool diag = (d == 0);
-        const int k_begin = diag ? 1 : 0, k_end = diag ? 17 : 32;
-        for (int k = k_begin; k < k_end; ++k) {
-            const int jj = (lane + k) & 31;
-            const int ja = J * kTile + jj;
-            const double dx = xi - S.x[ja], dy = yi - S.y[ja], dz = zi - S.z[ja];
-            const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-            bool on = !((m_excl >> jj) & 1u);
-            if (diag && k == 16) on = on && (lane < 16);
-            if (CUTOFF) on = on && !(r2 > S.r2_max);
-            if (on) {
-                const unsigned long long p = atomicAdd(cursor, 1ull);
-                if ((long long)p < capacity) {
-                    out_i[p] = min(ia, ja);
-                    out_j[p] = max(ia, ja);
-                    out_14[p] = (m_14 >> jj) & 1u;
+        const bool self = q < kNI;
+        for (int a = 0; a < kNI; ++a) {
+            if (self && a > q) continue;
+            const int ia = (it.S * kNI + a) * kTile + lane;
+            const double xi = S.x[ia], yi = S.y[ia], zi = S.z[ia];
+            const uint32_t m_excl = mi >= 0 ? masks[mi].excl[a][lane] : 0u;
+            const uint32_t m_14 = mi >= 0 ? masks[mi].f14[a][lane] : 0u;
+            for (int k = 0; k < 32; ++k) {
+                const int jj = (lane + k) & 31;
+                const int ja = J * kTile + jj;
+                const double dx = xi - S.x[ja], dy = yi - S.y[ja], dz = zi - S.z[ja];
+                const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                bool on = !((m_excl >> jj) & 1u);
+                if (self && a == q) on = on && (jj > lane);
+                if (CUTOFF) on = on && !(r2 > S.r2_max);
+                if (on) {
+                    const unsigned long long p = atomicAdd(cursor, 1ull);
+                    if ((long long)p < capacity) {
+                        out_i[p] = min(ia, ja);
+                        out_j[p] = max(ia, ja);
+                        out_14[p] = (m_14 >> jj) & 1u;
+                    }
                 }
             }
         }
