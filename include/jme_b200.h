@@ -144,6 +144,15 @@ int jme_set_coords_device(jme_handle_t* h, const double* d_xyz, int64_t n_atoms)
 int jme_eval_device(jme_handle_t* h, int want_gradient, double* d_out);
 int64_t jme_eval_out_size(const jme_handle_t* h, int want_gradient);   /* doubles */
 
+/* The reference's coordinate-wise minimizer loop, restated natively so that BASELINE config 4 (energy calls per
+ * second inside the optimizer) can be measured without a JVM: GradientDescentMinimizer.minimize
+ * (minimizer/GradientDescentMinimizer.java:49-105) with no constraint - per coordinate: move, full energy,
+ * keep / undo, slope *= 1.05 / 0.9; one initialising sweep, then `max_steps` sweeps or |dE| <= threshold.
+ * Every trial is one jme_set_coord1 + one energy evaluation on the device.  xyz_inout: AoS [n][3], updated in
+ * place; step_energies[k] = energy after step k (k = 0 is the initial energy), at most `capacity` entries. */
+int jme_gd_minimize(jme_handle_t* h, int max_steps, double step_size, double threshold, double* xyz_inout,
+                    int64_t* energy_calls, int* steps_done, double* step_energies, int capacity);
+
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 uint64_t jme_launch_count(const jme_handle_t* h);
 

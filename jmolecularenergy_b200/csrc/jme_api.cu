@@ -79,7 +79,8 @@ struct jme_handle {
     CellPlan cells;
 
     double* d_out = nullptr;
-    double* h_out = nullptr;   // pinned header
+    double* h_out = nullptr;   // pinned, mapped header: reduce_kernel writes the results straight into it
+    double* h_out_dev = nullptr;   // device alias of h_out
     uint64_t last_pairs = 0, last_cand = 0;
 
     // profiling ring: 3 events per evaluation (before build, before pairs, after pairs)
@@ -413,6 +414,7 @@ int enqueue_eval(jme_handle* h, bool grad, double* d_out_user) {
     A.unit_den = h->unit == JME_KCAL_PER_MOL ? 1.0 : kUnitToJoule[h->unit];
     A.want_grad = grad ? 1 : 0;
     A.out = d_out_user ? d_out_user : h->d_out;
+    A.out_host = d_out_user ? nullptr : h->h_out_dev;
     const int grid = grad ? (h->ds.n + 31) / 32 + 1 : 1;
     reduce_kernel<<<grid, kReduceWarps * 32, 0, h->stream>>>(A);
     ++h->launches;
@@ -421,7 +423,8 @@ int enqueue_eval(jme_handle* h, bool grad, double* d_out_user) {
 }
 
 int finish_host(jme_handle* h, bool grad, double* total, double* comps, double* grad_xyz) {
-    JME_CUDA(h, cudaMemcpyAsync(h->h_out, h->d_out, kOutHeader * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    // the 10-double header arrives through mapped pinned memory (written by reduce_kernel); only the gradient
+    // needs a copy
     if (grad && grad_xyz && h->hs.n > 0)
         JME_CUDA(h, cudaMemcpyAsync(grad_xyz, h->d_out + kOutHeader, 3 * (size_t)h->hs.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     JME_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -488,7 +491,8 @@ int jme_create(const jme_system_t* sys, jme_handle_t** out) {
     if ((rc = dev_upload(h, &h->d_table, table))) return bail(rc);
     if ((rc = dev_alloc(h, &h->d_xyz_stage, 3 * (size_t)std::max(1, n)))) return bail(rc);
     if ((rc = dev_alloc(h, &h->d_out, kOutHeader + 3 * (size_t)std::max(1, n)))) return bail(rc);
-    if (cudaMallocHost(&h->h_out, kOutHeader * sizeof(double)) != cudaSuccess) { h->err = "cudaMallocHost failed"; return bail(JME_ERR_CUDA); }
+    if (cudaHostAlloc(&h->h_out, kOutHeader * sizeof(double), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(&h->h_out_dev, h->h_out, 0) != cudaSuccess) { h->err = "cudaHostAlloc (mapped) failed"; return bail(JME_ERR_CUDA); }
 
     h->ds.n = n; h->ds.n_pad = n_pad; h->ds.n_blocks = n_pad / kTile; h->ds.n_types = std::max(1, hs.n_types);
     h->ds.x = h->d_x; h->ds.y = h->d_y; h->ds.z = h->d_z; h->ds.q = h->d_q; h->ds.type = h->d_type; h->ds.table = h->d_table;
@@ -626,6 +630,67 @@ int jme_energy_gradient(jme_handle_t* h, double* total, double comps[JME_N_COMPO
     int rc = enqueue_eval(h, true, nullptr);
     if (rc) return rc;
     return finish_host(h, true, total, comps, grad_xyz);
+}
+
+int jme_gd_minimize(jme_handle_t* h, int max_steps, double step_size, double threshold, double* xyz,
+                    int64_t* energy_calls, int* steps_done, double* step_energies, int capacity) {
+    if (!h || !xyz) return JME_ERR_INVALID;
+    JME_CUDA(h, cudaSetDevice(h->device));
+    const int64_t n = h->hs.n;
+    int rc = jme_set_coords(h, xyz, n);
+    if (rc) return rc;
+    int64_t calls = 0;
+    auto energy = [&](double& e) -> int {
+        ++calls;
+        int r = enqueue_eval(h, false, nullptr);
+        if (r) return r;
+        return finish_host(h, false, &e, nullptr, nullptr);
+    };
+    auto move = [&](int64_t a, int i, double d) -> int {          // movePoint, GradientDescentMinimizer.java:107-115
+        xyz[3 * a + i] += d;
+        return jme_set_coord1(h, a, i, xyz[3 * a + i]);
+    };
+    int step = 0;
+    std::vector<double> grads(3 * (size_t)n, step_size);           // :51-54
+    bool initialized = false;
+    double last_energy = 0, previous_step_energy = 0;
+    if ((rc = energy(last_energy))) return rc;                     // :56
+    int n_log = 0;
+    if (step_energies && n_log < capacity) step_energies[n_log++] = last_energy;   // onStepConsumer(0, E)
+    while (step < max_steps) {
+        if (step != 0 && std::fabs(previous_step_energy - last_energy) <= threshold) break;   // :62-64
+        previous_step_energy = last_energy;
+        for (int64_t a = 0; a < n; ++a)
+            for (int i = 0; i < 3; ++i) {
+                double& g = grads[3 * a + i];
+                if (g == 0) continue;
+                const double mag = std::min(std::fabs(step_size * g), .3);
+                const double distance = mag * ((g > 0) - (g < 0));             // Math.signum
+                if ((rc = move(a, i, distance))) return rc;
+                double e;
+                if ((rc = energy(e))) return rc;
+                const double difference = e - last_energy;                       // :78
+                g = -difference / (distance == 0 ? 1 : distance);               // :79
+                if (!initialized) {
+                    if ((rc = move(a, i, -distance))) return rc;
+                } else if (difference > 0) {
+                    if ((rc = move(a, i, -distance))) return rc;
+                    g = g * 0.9;
+                } else {
+                    last_energy += difference;
+                    g = g * 1.05;
+                }
+            }
+        if (!initialized) {
+            initialized = true;
+        } else {
+            ++step;
+            if (step_energies && n_log < capacity) step_energies[n_log++] = last_energy;
+        }
+    }
+    if (energy_calls) *energy_calls = calls;
+    if (steps_done) *steps_done = step;
+    return JME_OK;
 }
 
 int64_t jme_eval_out_size(const jme_handle_t* h, int want_gradient) {

@@ -501,6 +501,7 @@ struct ReduceArgs {
     double unit_num, unit_den;      // (v * num) / den, ForceField.java:157; both 1 for kcal/mol
     int want_grad;
     double* out;                    // [0] total [1..7] comps [8] pairs evaluated [9] candidates [10..] gradient AoS
+    double* out_host;               // optional: mapped pinned host copy of the 10-double header (zero-copy result)
 };
 constexpr int kOutHeader = 10;
 
@@ -592,6 +593,10 @@ reduce_kernel(ReduceArgs A) {
         A.out[0] = total;
         A.out[8] = (double)s_c[0][0];
         A.out[9] = (double)s_c[1][0];
+        if (A.out_host) {
+            for (int c = 0; c < kOutHeader; ++c) A.out_host[c] = A.out[c];
+            __threadfence_system();
+        }
     }
 }
 

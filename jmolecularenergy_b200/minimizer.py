@@ -99,6 +99,39 @@ class GradientDescentMinimizer(EnergyMinimizer):
                     self.onStepConsumer(self.step, lastEnergy)
 
 
+class NativeGradientDescentMinimizer(EnergyMinimizer):
+    """The same loop as :class:`GradientDescentMinimizer`, run inside ``libjme_b200.so`` (``jme_gd_minimize``): no
+    per-call Python / ctypes overhead, which is what BASELINE config 4 (energy calls per second inside the
+    optimizer) measures.  Constraints are not supported on this path."""
+
+    def __init__(self, forcefield):
+        super().__init__()
+        self.forcefield = forcefield
+        self.energyCalls = 0
+        self.stepEnergies = []
+
+    def minimize(self, container, maximumSteps: int, stepSize: float, threshold: float) -> None:
+        import ctypes as C
+        if self.constraint is not None:
+            raise NotImplementedError("constraints are evaluated on the host: use GradientDescentMinimizer")
+        st = self.forcefield._state(container)
+        st.sync_options(self.forcefield, self.forcefield.path)
+        xyz = np.ascontiguousarray(container.xyz, dtype=np.float64)
+        calls, steps = C.c_int64(), C.c_int()
+        log = np.zeros(maximumSteps + 2)
+        st.check(st.L.jme_gd_minimize(st.h, int(maximumSteps), float(stepSize), float(threshold),
+                                      xyz.ctypes.data_as(C.POINTER(C.c_double)), C.byref(calls), C.byref(steps),
+                                      log.ctypes.data_as(C.POINTER(C.c_double)), log.shape[0]))
+        container.xyz[:] = xyz
+        st.shadow = xyz.reshape(-1).copy()
+        self.energyCalls = int(calls.value)
+        self.step = int(steps.value)
+        self.stepEnergies = log[:self.step + 1].tolist()
+        if self.onStepConsumer is not None:
+            for k, e in enumerate(self.stepEnergies):
+                self.onStepConsumer(k, e)
+
+
 class _AdamOptimizer:
     """``AdamMinimizer.AdamOptimizer`` (``AdamMinimizer.java:131-161``)."""
 

@@ -30,7 +30,7 @@ def run(name, s, cutoff, path, grad=True, reps=20):
           f"{pe.value/(k*1e-3):.3e} pairs/s  {flop*pe.value/(k*1e-3)/1e12:6.2f} TFLOP/s  call wall {wall*1e6:8.1f} us")
     st.close()
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     run("water3k allpairs", systems.water_box(1000), 0.0, "allpairs")
     run("water3k allpairs", systems.water_box(1000), 0.0, "allpairs", grad=False)
     run("water5k allpairs", systems.water_box(1667), 0.0, "allpairs")
@@ -39,3 +39,23 @@ if __name__ == "__main__":
     run("solvated25k allpairs cut10", systems.solvated_chains(24999), 10.0, "allpairs")
     run("solvated25k cells cut10", systems.solvated_chains(24999), 10.0, "cells")
     run("ions125k cells cut10", systems.ion_box(50), 10.0, "cells")
+
+
+def opt5k(n_waters=1667, max_steps=0):
+    """BASELINE config 4: the reference's GradientDescentMinimizer loop (natively restated, jme_gd_minimize) on a
+    5 001-atom water box: energy calls per second (each call = one coordinate update + one full energy)."""
+    from jmolecularenergy_b200 import MMFF94, NativeGradientDescentMinimizer
+    s = systems.water_box(n_waters)
+    ff = MMFF94(False)
+    ff.assignParameters(s)
+    m = NativeGradientDescentMinimizer(ff)
+    t0 = time.perf_counter()
+    m.minimize(s, max_steps, 0.01, 1e-4)
+    dt = time.perf_counter() - t0
+    pairs = ff.calculateComponents(s)["pairs"]
+    print(f"opt5k: atoms {s.n_atoms} steps {m.step} energy calls {m.energyCalls} in {dt:.3f} s -> {m.energyCalls/dt:.0f} calls/s, "
+          f"{m.energyCalls*pairs/dt:.3e} pair-energies/s; E {m.stepEnergies[0]:.3f} -> {m.stepEnergies[-1]:.3f}")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "opt":
+    opt5k(max_steps=int(sys.argv[2]) if len(sys.argv) > 2 else 0)
