@@ -83,11 +83,26 @@ struct jme_handle {
     double* h_out_dev = nullptr;   // device alias of h_out
     uint64_t last_pairs = 0, last_cand = 0;
 
+    // CUDA graphs of the all-pairs evaluation sequence {nonbonded | bonded} -> reduce (launch-bound small
+    // systems): one per (gradient?, output buffer); rebuilt whenever anything baked into the kernel arguments changes
+    struct EvalGraph { cudaGraphExec_t exec = nullptr; uint64_t epoch = 0; double* out = nullptr; cudaStream_t stream = nullptr; };
+    EvalGraph graphs[2];
+    uint64_t graph_epoch = 1;
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t fork_event = nullptr, join_event = nullptr;
+    bool use_graphs = true;
+
     // profiling ring: 3 events per evaluation (before build, before pairs, after pairs)
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;
     size_t prof_used = 0;     // evaluations recorded since the last read
-    ~jme_handle() { for (cudaEvent_t e : prof_events) cudaEventDestroy(e); }
+    ~jme_handle() {
+        for (cudaEvent_t e : prof_events) cudaEventDestroy(e);
+        for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+        if (fork_event) cudaEventDestroy(fork_event);
+        if (join_event) cudaEventDestroy(join_event);
+        if (side_stream) cudaStreamDestroy(side_stream);
+    }
 };
 
 namespace {
@@ -331,6 +346,7 @@ int ensure_plan(jme_handle* h) {
     h->ds.r2_max = h->cutoff > 0 ? cutoff_r2_threshold(h->cutoff) : 0.0;
     h->ds.ele_scale = kEleC / h->dielectric;
     h->plan_dirty = false;
+    ++h->graph_epoch;
     return JME_OK;
 }
 
@@ -375,14 +391,28 @@ int launch_ap(jme_handle* h) {
     return n_items < 148ll * 8 * 3 ? launch_ap_k<GRAD, CUTOFF, kApWarps>(h) : launch_ap_k<GRAD, CUTOFF, 1>(h);
 }
 
-// Enqueue one evaluation; results land in h->d_out (or d_out_user).
-int enqueue_eval(jme_handle* h, bool grad, double* d_out_user) {
+// The launches of one evaluation; results land in h->d_out (or d_out_user).  With `fork` the bonded kernel runs
+// on a side stream next to the nonbonded kernel (used while capturing the evaluation into a CUDA graph).
+int enqueue_launches(jme_handle* h, bool grad, double* d_out_user, bool fork) {
     int rc;
-    if (!h->coords_set) return fail(h, JME_ERR_NOT_ASSIGNED, "MMFF94 parameters need to be assigned first (no coordinates set)");
-    if ((rc = ensure_plan(h))) return rc;
     const bool cut = h->cutoff > 0;
     ReduceArgs A{};
     A.n = h->ds.n; A.n_pad = h->ds.n_pad;
+    const long long n_terms = h->term_end - h->term_begin;
+    auto launch_bonded = [&](cudaStream_t st) -> int {
+        if (n_terms <= 0) return JME_OK;
+        if (grad) bonded_kernel<true><<<h->n_bpart, kBondedThreads, 0, st>>>(h->ds, h->bt, h->term_begin, h->term_end, h->d_slots, h->d_bpart);
+        else bonded_kernel<false><<<h->n_bpart, kBondedThreads, 0, st>>>(h->ds, h->bt, h->term_begin, h->term_end, h->d_slots, h->d_bpart);
+        ++h->launches;
+        JME_CUDA(h, cudaGetLastError());
+        return JME_OK;
+    };
+    if (fork && n_terms > 0) {
+        JME_CUDA(h, cudaEventRecord(h->fork_event, h->stream));
+        JME_CUDA(h, cudaStreamWaitEvent(h->side_stream, h->fork_event, 0));
+        if ((rc = launch_bonded(h->side_stream))) return rc;
+        JME_CUDA(h, cudaEventRecord(h->join_event, h->side_stream));
+    }
     cudaEvent_t* pe = prof_slot(h);
     if (pe) cudaEventRecord(pe[0], h->stream);
     if (h->active_path == JME_PATH_ALLPAIRS) {
@@ -400,13 +430,8 @@ int enqueue_eval(jme_handle* h, bool grad, double* d_out_user) {
         A.epart = h->cells.d_epart; A.cpart = h->cells.d_cpart; A.n_epart = h->cells.n_epart;
     }
     if (pe) { cudaEventRecord(pe[2], h->stream); ++h->prof_used; }
-    const long long n_terms = h->term_end - h->term_begin;
-    if (n_terms > 0) {
-        if (grad) bonded_kernel<true><<<h->n_bpart, kBondedThreads, 0, h->stream>>>(h->ds, h->bt, h->term_begin, h->term_end, h->d_slots, h->d_bpart);
-        else bonded_kernel<false><<<h->n_bpart, kBondedThreads, 0, h->stream>>>(h->ds, h->bt, h->term_begin, h->term_end, h->d_slots, h->d_bpart);
-        ++h->launches;
-        JME_CUDA(h, cudaGetLastError());
-    }
+    if (fork && n_terms > 0) JME_CUDA(h, cudaStreamWaitEvent(h->stream, h->join_event, 0));
+    else if ((rc = launch_bonded(h->stream))) return rc;
     A.slots = h->d_slots; A.slot_ptr = h->d_slot_ptr; A.slot_idx = h->d_slot_idx;
     A.slot_lo = h->slot_lo; A.slot_hi = h->slot_hi;
     A.bpart = h->d_bpart; A.n_bpart = n_terms > 0 ? h->n_bpart : 0;
@@ -419,6 +444,50 @@ int enqueue_eval(jme_handle* h, bool grad, double* d_out_user) {
     reduce_kernel<<<grid, kReduceWarps * 32, 0, h->stream>>>(A);
     ++h->launches;
     JME_CUDA(h, cudaGetLastError());
+    return JME_OK;
+}
+
+// Enqueue one evaluation.  All-pairs path without profiling: replay a captured CUDA graph.
+int enqueue_eval(jme_handle* h, bool grad, double* d_out_user) {
+    int rc;
+    if (!h->coords_set) return fail(h, JME_ERR_NOT_ASSIGNED, "MMFF94 parameters need to be assigned first (no coordinates set)");
+    if ((rc = ensure_plan(h))) return rc;
+    // (the legacy default stream cannot be captured)
+    if (h->ds.n == 0 || !h->use_graphs || h->profiling || h->active_path != JME_PATH_ALLPAIRS || h->stream == nullptr)
+        return enqueue_launches(h, grad, d_out_user, false);
+    jme_handle::EvalGraph& g = h->graphs[grad ? 1 : 0];
+    double* out = d_out_user ? d_out_user : h->d_out;
+    if (!g.exec || g.epoch != h->graph_epoch || g.out != out || g.stream != h->stream) {
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        if (!h->side_stream) {
+            JME_CUDA(h, cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+            JME_CUDA(h, cudaEventCreateWithFlags(&h->fork_event, cudaEventDisableTiming));
+            JME_CUDA(h, cudaEventCreateWithFlags(&h->join_event, cudaEventDisableTiming));
+        }
+        const uint64_t launches_before = h->launches;
+        cudaGraph_t graph = nullptr;
+        JME_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        rc = enqueue_launches(h, grad, d_out_user, true);
+        cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        h->launches = launches_before;
+        if (rc || ce != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            h->use_graphs = false;                 // fall back to plain launches for this handle
+            return rc ? rc : enqueue_launches(h, grad, d_out_user, false);
+        }
+        ce = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) {
+            g.exec = nullptr;
+            cudaGetLastError();
+            h->use_graphs = false;
+            return enqueue_launches(h, grad, d_out_user, false);
+        }
+        g.epoch = h->graph_epoch; g.out = out; g.stream = h->stream;
+    }
+    JME_CUDA(h, cudaGraphLaunch(g.exec, h->stream));
+    h->launches += 2 + ((h->term_end - h->term_begin) > 0 ? 1 : 0);     // kernels inside the graph
     return JME_OK;
 }
 
@@ -535,6 +604,7 @@ int jme_set_options(jme_handle_t* h, double cutoff, double dielectric, int energ
     h->unit = energy_unit;
     h->ds.r2_max = cutoff > 0 ? cutoff_r2_threshold(cutoff) : 0.0;
     h->ds.ele_scale = kEleC / dielectric;
+    ++h->graph_epoch;          // cutoff threshold, dielectric scale and unit factors are kernel arguments
     return JME_OK;
 }
 

@@ -96,10 +96,17 @@ __global__ void __launch_bounds__(256) bbox_kernel(DeviceSystem S, double* __res
 }
 
 __global__ void grid_setup_kernel(const double* __restrict__ part, int n_part, double cutoff, int max_cells, GridParams* g) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    // one warp: lanes stride over the per-block bounding boxes, shuffle min/max, lane 0 derives the grid
+    const int lane = threadIdx.x;
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-    for (int b = 0; b < n_part; ++b)
+    for (int b = lane; b < n_part; b += 32)
         for (int c = 0; c < 3; ++c) { lo[c] = fmin(lo[c], part[6 * b + c]); hi[c] = fmax(hi[c], part[6 * b + 3 + c]); }
+    for (int c = 0; c < 3; ++c)
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = fmin(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = fmax(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+        }
+    if (lane != 0) return;
     double ext[3], extent = 0;
     for (int c = 0; c < 3; ++c) { ext[c] = fmax(hi[c] - lo[c], 0.0); extent = fmax(extent, ext[c]); }
     // cell edge: half the cutoff (5x5x5 stencil, about 27 % of it inside the sphere before row culling),
