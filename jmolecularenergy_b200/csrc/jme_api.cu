@@ -85,7 +85,7 @@ struct jme_handle {
 
     // CUDA graphs of the all-pairs evaluation sequence {nonbonded | bonded} -> reduce (launch-bound small
     // systems): one per (gradient?, output buffer); rebuilt whenever anything baked into the kernel arguments changes
-    struct EvalGraph { cudaGraphExec_t exec = nullptr; uint64_t epoch = 0; double* out = nullptr; cudaStream_t stream = nullptr; };
+    struct EvalGraph { cudaGraphExec_t exec = nullptr; uint64_t epoch = 0; double* out = nullptr; cudaStream_t stream = nullptr; uint64_t kernels = 0; };
     EvalGraph graphs[2];
     uint64_t graph_epoch = 1;
     cudaStream_t side_stream = nullptr;
@@ -424,6 +424,7 @@ int enqueue_launches(jme_handle* h, bool grad, double* d_out_user, bool fork) {
         A.epart = h->d_epart; A.cpart = h->d_cpart; A.n_epart = h->n_epart;
     } else {
         if ((rc = run_cell_sort(h->cells, h->ds, h->stream, h->launches, h->err))) return rc;
+        if ((rc = run_cell_lists(h->cells, h->ds, h->stream, h->launches, h->err))) return rc;
         if (pe) cudaEventRecord(pe[1], h->stream);
         if ((rc = run_cell_path(h->cells, h->ds, grad, h->stream, h->launches, h->err))) return rc;
         A.gpart = nullptr; A.n_slots = 0; A.direct = h->cells.d_grad;
@@ -453,8 +454,10 @@ int enqueue_eval(jme_handle* h, bool grad, double* d_out_user) {
     if (!h->coords_set) return fail(h, JME_ERR_NOT_ASSIGNED, "MMFF94 parameters need to be assigned first (no coordinates set)");
     if ((rc = ensure_plan(h))) return rc;
     // (the legacy default stream cannot be captured)
-    if (h->ds.n == 0 || !h->use_graphs || h->profiling || h->active_path != JME_PATH_ALLPAIRS || h->stream == nullptr)
+    if (h->ds.n == 0 || !h->use_graphs || h->profiling || h->stream == nullptr)
         return enqueue_launches(h, grad, d_out_user, false);
+    // the captured sequence of the cell path always contains the sort and the list build
+    if (h->active_path == JME_PATH_CELLS) h->cells.coords_changed();
     jme_handle::EvalGraph& g = h->graphs[grad ? 1 : 0];
     double* out = d_out_user ? d_out_user : h->d_out;
     if (!g.exec || g.epoch != h->graph_epoch || g.out != out || g.stream != h->stream) {
@@ -469,6 +472,7 @@ int enqueue_eval(jme_handle* h, bool grad, double* d_out_user) {
         JME_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         rc = enqueue_launches(h, grad, d_out_user, true);
         cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        g.kernels = h->launches - launches_before;
         h->launches = launches_before;
         if (rc || ce != cudaSuccess || !graph) {
             if (graph) cudaGraphDestroy(graph);
@@ -487,7 +491,7 @@ int enqueue_eval(jme_handle* h, bool grad, double* d_out_user) {
         g.epoch = h->graph_epoch; g.out = out; g.stream = h->stream;
     }
     JME_CUDA(h, cudaGraphLaunch(g.exec, h->stream));
-    h->launches += 2 + ((h->term_end - h->term_begin) > 0 ? 1 : 0);     // kernels inside the graph
+    h->launches += g.kernels;                                            // kernels inside the graph
     return JME_OK;
 }
 
@@ -501,6 +505,9 @@ int finish_host(jme_handle* h, bool grad, double* total, double* comps, double* 
     if (comps) for (int c = 0; c < JME_N_COMPONENTS; ++c) comps[c] = h->h_out[1 + c];
     h->last_pairs = (uint64_t)h->h_out[8];
     h->last_cand = (uint64_t)h->h_out[9];
+    if (h->active_path == JME_PATH_CELLS && cell_overflowed(h->cells))
+        return fail(h, JME_ERR_UNSUPPORTED, "a cutoff sphere holds more atoms than the survivor-list capacity (" +
+                    std::to_string(h->cells.list_cap) + "); the system is too dense for the cell path at this cutoff");
     return JME_OK;
 }
 

@@ -8,14 +8,17 @@
 //   3. scatter to cells, then rank inside each cell by original atom index, so the sorted order (and
 //      with it every later summation order) is deterministic; SoA gather into sorted arrays (FP64
 //      positions/charges, type, and an FP32 copy of the positions relative to the grid origin)
-//   4. cells_pair_kernel: one warp per atom i.  Lanes scan the candidate atoms of the neighbouring cell
-//      rows with a conservative FP32 distance test (superset of the true pair set), compact the
-//      survivors into a per-warp shared-memory queue, and every time 32 are queued the warp evaluates
-//      them with all lanes busy: exact FP64 predicate (bit-identical to the reference's
-//      sqrt(dx*dx+dy*dy+dz*dz) > cutoff via the r^2 threshold), exclusion / 1-4 lookup, vdW + Coulomb.
+//   4a. cells_list_kernel (the neighbour-list build, integer / FP32 only): one warp per CELL scans the 25
+//      neighbour cell rows once for all atoms of the cell - the row ranges are flattened into one virtual index
+//      space so that every trip tests 64 candidates (coalesced FP32 positions relative to the grid origin)
+//      against each atom of the cell with a conservative distance test (padded margins: a superset of the
+//      true pair set) and appends the survivors to that atom's survivor list (fixed capacity, streaming stores).
+//   4b. cells_pair_kernel (FP64): one warp per atom evaluates its list 32 entries at a time with all lanes busy:
+//      exact predicate (bit-identical to the reference's sqrt(dx*dx+dy*dy+dz*dz) > cutoff via the r^2
+//      threshold), exclusion / 1-4 lookup, vdW + Coulomb; list entries are fetched two trips ahead and the
+//      atoms they name one trip ahead (in-order issue: a load must be issued a trip before its first use).
 //      Each pair is evaluated from both of its atoms (no Newton's third law): no scatter, no atomics,
-//      deterministic; energies are halved.  The row ranges of an atom are computed lane-parallel (one
-//      lane per neighbour cell row, culled against the cutoff sphere in FP32 with padded margins).
+//      deterministic; energies are halved.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -249,6 +252,10 @@ __global__ void cell_rank_gather_kernel(DeviceSystem S, CellArrays C) {
 // ---- 4. pairs ----------------------------------------------------------------------------------
 struct CellPairArgs {
     int i_begin, i_end;            // sorted positions handled by this shard
+    const unsigned int* list;      // [n][cap] survivor lists (cells_list_kernel)
+    const int* count;              // [n]
+    int cap;
+    int group;                     // atoms a warp takes per visit (1..32)
     double* grad;                  // [3][n_pad] by original atom index
     double* epart;                 // [warps][2]
     unsigned long long* cpart;     // [warps][2]
@@ -256,7 +263,130 @@ struct CellPairArgs {
     int* out_i; int* out_j; unsigned char* out_14; long long capacity; unsigned long long* cursor;
 };
 
-constexpr int kQueue = 128;          // per-warp candidate ring (power of two)
+// ---- 4a. survivor lists --------------------------------------------------------------------------
+// One warp per CELL.  The 25 neighbour cell rows are scanned once for all atoms of the cell: a trip loads 64
+// candidate positions (FP32, coalesced) and tests them against every atom i of the cell (i broadcast from
+// shared memory) with the conservative FP32 distance test; survivors are appended to the survivor list of i
+// (fixed capacity per atom, L2-resident while hot).  Integer / FP32 only, few registers, high occupancy.
+#ifndef JME_LIST_WARPS
+#define JME_LIST_WARPS 8
+#endif
+#ifndef JME_LIST_MIN_BLOCKS
+#define JME_LIST_MIN_BLOCKS 6
+#endif
+constexpr int kListWarps = JME_LIST_WARPS;
+constexpr int kListThreads = kListWarps * 32;
+
+struct CellListArgs {
+    int i_begin, i_end;            // sorted positions handled by this shard
+    unsigned int* list;            // [n][cap] survivor lists by sorted position
+    int* count;                    // [n] list lengths (clamped to cap)
+    int cap;
+    int parts;                     // warps sharing one cell (1 for large systems)
+    int* overflow;                 // set to 1 if any list had to be truncated
+};
+
+__global__ void __launch_bounds__(kListThreads, JME_LIST_MIN_BLOCKS)
+cells_list_kernel(CellArrays C, CellListArgs P) {
+    __shared__ float4 s_fi[kListWarps][32];
+    __shared__ int s_jb[kListWarps][32];        // first candidate of neighbour row r
+    __shared__ int s_off[kListWarps][33];       // exclusive prefix of the row lengths (virtual candidate index)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4* fis = s_fi[warp];
+    int* jbs = s_jb[warp];
+    int* off = s_off[warp];
+    const GridParams g = *C.grid;
+    const int gw = blockIdx.x * kListWarps + warp;
+    const int n_warps = gridDim.x * kListWarps;
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    const int width = 2 * g.reach + 1;
+    const int n_rows = width * width;          // <= 25: reach <= 2 by construction (edge >= cutoff / 2)
+    const float4* __restrict__ fxyz = C.fxyz;
+
+    // work item = (cell, part): a cell's atoms are split among P.parts warps when there are few cells
+    for (int w = gw; w < g.ncell * P.parts; w += n_warps) {
+        const int c = w / P.parts, part = w % P.parts;
+        const int c0 = C.start[c], c1 = C.start[c + 1];
+        const int per = (c1 - c0 + P.parts - 1) / P.parts;
+        const int a0 = c0 + part * per;
+        const int s0 = max(a0, P.i_begin), s1 = min(min(c1, a0 + per), P.i_end);
+        if (s0 >= s1) continue;
+        const int cx = c % g.nx, cy = (c / g.nx) % g.ny, cz = c / (g.nx * g.ny);
+        int total;
+        {   // candidate range of neighbour row `lane` (shared by all atoms of the cell), and the prefix sums that
+            // flatten the <= 25 ranges into one virtual index space so that every trip has all 64 slots filled
+            int jb = 0, len = 0;
+            if (lane < n_rows) {
+                const int y2 = cy + lane % width - g.reach, z2 = cz + lane / width - g.reach;
+                if (y2 >= 0 && y2 < g.ny && z2 >= 0 && z2 < g.nz) {
+                    const int x0 = max(cx - g.reach, 0), x1 = min(cx + g.reach, g.nx - 1);
+                    const int row = (z2 * g.ny + y2) * g.nx;
+                    jb = C.start[row + x0];
+                    len = C.start[row + x1 + 1] - jb;
+                }
+            }
+            int incl = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            total = __shfl_sync(0xffffffffu, incl, 31);
+            __syncwarp();
+            jbs[lane] = jb;
+            off[lane] = incl - len;
+            if (lane == 31) off[32] = incl;
+        }
+        for (int ch = s0; ch < s1; ch += 32) {              // at most 32 atoms of the cell at a time
+            const int nc = min(32, s1 - ch);
+            __syncwarp();
+            fis[lane] = fxyz[min(ch + lane, s1 - 1)];
+            int my_cnt = 0;                                   // lane il holds the list length of atom ch + il
+            __syncwarp();
+            int r0 = 0, r1 = 0;                               // row of this lane's two virtual indices (monotone)
+            for (int vb = 0; vb < total; vb += 64) {
+                const int v0i = vb + lane, v1i = v0i + 32;
+                const bool v0 = v0i < total, v1 = v1i < total;
+                while (r0 < 31 && v0i >= off[r0 + 1]) ++r0;
+                while (r1 < 31 && v1i >= off[r1 + 1]) ++r1;
+                const int j0 = v0 ? jbs[r0] + (v0i - off[r0]) : -1;
+                const int j1 = v1 ? jbs[r1] + (v1i - off[r1]) : -1;
+                float4 a0 = fxyz[max(j0, 0)];
+                float4 a1 = fxyz[max(j1, 0)];
+                if (!v0) a0.x = 1e18f;                        // never passes the distance test
+                if (!v1) a1.x = 1e18f;
+                for (int il = 0; il < nc; ++il) {
+                    const float4 fi = fis[il];
+                    const float x0 = fi.x - a0.x, y0 = fi.y - a0.y, z0 = fi.z - a0.z;
+                    const float x1 = fi.x - a1.x, y1 = fi.y - a1.y, z1 = fi.z - a1.z;
+                    // the atom itself (distance 0) passes too; the evaluation kernel drops it
+                    const bool h0 = (x0 * x0 + y0 * y0 + z0 * z0) <= g.r2f_max;
+                    const bool h1 = (x1 * x1 + y1 * y1 + z1 * z1) <= g.r2f_max;
+                    const unsigned int m0 = __ballot_sync(0xffffffffu, h0);
+                    const unsigned int m1 = __ballot_sync(0xffffffffu, h1);
+                    if ((m0 | m1) == 0) continue;
+                    const int cnt = __shfl_sync(0xffffffffu, my_cnt, il);
+                    const int c0n = __popc(m0), c1n = __popc(m1);
+                    if (cnt + c0n + c1n <= P.cap) {
+                        unsigned int* dst = P.list + (size_t)(ch + il) * P.cap + cnt;
+                        if (h0) __stcs(dst + __popc(m0 & lt_mask), (unsigned int)j0);
+                        if (h1) __stcs(dst + c0n + __popc(m1 & lt_mask), (unsigned int)j1);
+                        if (lane == il) my_cnt += c0n + c1n;
+                    } else if (lane == 0) {
+                        *P.overflow = 1;
+                    }
+                }
+            }
+            if (lane < nc) P.count[ch + lane] = my_cnt;
+        }
+    }
+}
+
+// ---- 4b. evaluation --------------------------------------------------------------------------------
+// One warp per atom i: its survivor list is evaluated 32 entries at a time (all lanes busy):
+// exact FP64 predicate (bit-identical to the reference's sqrt(dx*dx+dy*dy+dz*dz) > cutoff via the r^2
+// threshold), exclusion / 1-4 lookup, vdW + Coulomb; the gradient of i stays in registers.  Every pair is
+// evaluated from both of its atoms: no scatter, no atomics, deterministic.
 
 template <bool GRAD, bool EMIT>
 __global__ void __launch_bounds__(kCellThreads, JME_CELL_MIN_BLOCKS)
@@ -264,161 +394,120 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PairConst* s_table = reinterpret_cast<PairConst*>(smem_raw);
     const int TT = S.n_types * S.n_types;
-    unsigned int* s_queue = reinterpret_cast<unsigned int*>(s_table + TT);
-    int2* s_rows = reinterpret_cast<int2*>(s_queue + kCellWarps * kQueue);
-    unsigned int* s_excl = reinterpret_cast<unsigned int*>(s_rows + kCellWarps * 32);
+    unsigned int* s_excl = reinterpret_cast<unsigned int*>(s_table + TT);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned int* queue = s_queue + warp * kQueue;
-    int2* rows = s_rows + warp * 32;
     unsigned int* excl = s_excl + warp * 32;
     for (int t = threadIdx.x; t < TT; t += kCellThreads) s_table[t] = S.table[t];
     __syncthreads();
 
-    const GridParams g = *C.grid;
     const int gw = blockIdx.x * kCellWarps + warp;
     const int n_warps = gridDim.x * kCellWarps;
-    const unsigned int lt_mask = (1u << lane) - 1u;
-    const int width = 2 * g.reach + 1;
-    const int n_rows = width * width;          // <= 25: reach <= 2 by construction (edge >= cutoff / 2)
     const double2* __restrict__ sxy = C.sxy;
     const double2* __restrict__ szq = C.szq;
-    const float4* __restrict__ fxyz = C.fxyz;
     const int* __restrict__ stype = C.stype;
     const int* __restrict__ orig = C.orig;
 
-    double ev_w = 0, ee_w = 0;
+    double ev = 0, ee = 0;                       // per-lane partial sums over everything this warp does
     unsigned long long n_eval_w = 0, n_cand_w = 0;
 
-    for (int i = P.i_begin + gw; i < P.i_end; i += n_warps) {
-        const double2 pi_xy = sxy[i], pi_zq = szq[i];
-        const float4 fi = fxyz[i];
+    // a warp takes 32 consecutive (cell-sorted) atoms at a time: lane l fetches the per-atom data of atom
+    // base + l in one coalesced round, the atoms are then processed one after the other with that data
+    // broadcast by shuffles - no chain of dependent loads at the start of every atom
+    const int G = P.group;                      // atoms per warp visit (<= 32): small systems use small groups
+    for (int base = P.i_begin + G * gw; base < P.i_end; base += G * n_warps) {
+      const int im = min(base + lane, P.i_end - 1);
+      const int m_hits = P.count[im];
+      const int m_oi = orig[im];
+      const long long m_eb = C.excl_ptr[m_oi];
+      const int m_nex = (int)(C.excl_ptr[m_oi + 1] - m_eb);
+      const double2 m_xy = sxy[im], m_zq = szq[im];
+      const int m_t = stype[im];
+      const int n_here = min(G, P.i_end - base);
+      for (int il = 0; il < n_here; ++il) {
+        const int i = base + il;
+        const int n_hits = __shfl_sync(0xffffffffu, m_hits, il);
+        const unsigned int* __restrict__ list = P.list + (size_t)i * P.cap;
+        const int oi = __shfl_sync(0xffffffffu, m_oi, il);
+        const long long eb = __shfl_sync(0xffffffffu, m_eb, il);
+        const int n_excl = __shfl_sync(0xffffffffu, m_nex, il);
+        if (n_excl > 0) {
+            __syncwarp();
+            excl[lane] = lane < n_excl ? C.excl_ent[eb + lane] : 0xffffffffu;
+            __syncwarp();
+        }
+        double2 pi_xy, pi_zq;
+        pi_xy.x = __shfl_sync(0xffffffffu, m_xy.x, il); pi_xy.y = __shfl_sync(0xffffffffu, m_xy.y, il);
+        pi_zq.x = __shfl_sync(0xffffffffu, m_zq.x, il); pi_zq.y = __shfl_sync(0xffffffffu, m_zq.y, il);
         const double qi2 = 2.0 * S.ele_scale * pi_zq.y;      // doubled energies, see pair_terms
-        const PairConst* trow = s_table + stype[i] * S.n_types;
-        const int oi = orig[i];
-        const long long eb = C.excl_ptr[oi];
-        const int n_excl = (int)(C.excl_ptr[oi + 1] - eb);
-        const int ci = C.scell[i];
-        const int cx = ci % g.nx, cy = (ci / g.nx) % g.ny, cz = ci / (g.nx * g.ny);
+        const PairConst* trow = s_table + __shfl_sync(0xffffffffu, m_t, il) * S.n_types;
+        double gix = 0, giy = 0, giz = 0;
+        unsigned int n_eval = 0;
 
-        // ---- lane-parallel: the candidate range of neighbour cell row `lane`, culled against the sphere
-        {
-            int jb = 0, je = 0;
-            if (lane < n_rows) {
-                const int ddy = lane % width - g.reach, ddz = lane / width - g.reach;
-                const int y2 = cy + ddy, z2 = cz + ddz;
-                if (y2 >= 0 && y2 < g.ny && z2 >= 0 && z2 < g.nz) {
-                    // distance from the atom to the cell slabs y2 / z2 (0 inside), origin-relative FP32
-                    float my = 0.f, mz = 0.f;
-                    if (ddy > 0) my = y2 * g.edge_f - fi.y; else if (ddy < 0) my = fi.y - (y2 + 1) * g.edge_f;
-                    if (ddz > 0) mz = z2 * g.edge_f - fi.z; else if (ddz < 0) mz = fi.z - (z2 + 1) * g.edge_f;
-                    my = fmaxf(my, 0.f);
-                    mz = fmaxf(mz, 0.f);
-                    const float rem = g.cut2_pad_f - (my * my + mz * mz);
-                    if (rem >= 0.f) {
-                        const float xr = sqrtf(rem) * (1.0f + 1e-6f);
-                        int x0 = (int)floorf((fi.x - xr) * g.inv_edge_f - 1e-4f);
-                        int x1 = (int)floorf((fi.x + xr) * g.inv_edge_f + 1e-4f);
-                        x0 = max(max(x0, cx - g.reach), 0);
-                        x1 = min(min(x1, cx + g.reach), g.nx - 1);
-                        if (x0 <= x1) {
-                            const int row = (z2 * g.ny + y2) * g.nx;
-                            jb = C.start[row + x0];
-                            je = C.start[row + x1 + 1];
+        // software pipeline (issue is in order, so a load has to be issued a whole trip before its first use):
+        // list entries two trips ahead, the atoms they name one trip ahead, arithmetic on the current trip
+        auto entry = [&](int e) { return e < n_hits ? (int)__ldcs(list + e) : i; };
+        int jn = entry(lane), j2 = entry(32 + lane);
+        double2 n_xy = sxy[jn], n_zq = szq[jn];
+        int n_t = stype[jn];
+        for (int b = 0; b < n_hits; b += 32) {
+            const bool active = b + lane < n_hits;
+            const int jc = jn, tj = n_t;
+            const double2 pj_xy = n_xy, pj_zq = n_zq;
+            if (b + 32 < n_hits) {
+                jn = j2;                                       // arrived during the previous trip
+                n_xy = sxy[jn]; n_zq = szq[jn]; n_t = stype[jn];
+                j2 = entry(b + 64 + lane);
+            }
+            {
+                const double dx = pi_xy.x - pj_xy.x, dy = pi_xy.y - pj_xy.y, dz = pi_zq.x - pj_zq.x;
+                // strict double, left-to-right, no FMA: Point3d.distance squared
+                const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                bool on = active && jc != i && !(r2 > S.r2_max);     // the list holds the atom itself too
+                bool f14 = false;
+                int oj = 0;
+                if (EMIT) oj = orig[jc];
+                if (n_excl > 0) {                      // warp-uniform: the list belongs to atom i
+                    if (!EMIT) oj = orig[jc];
+                    const int n_sm = min(n_excl, 32);
+                    for (int e = 0; e < n_sm; ++e) {
+                        const unsigned int x = excl[e];
+                        if ((int)(x & ~kFlag14) == oj) {
+                            if (x & kFlag14) f14 = true; else on = false;
+                        }
+                    }
+                    for (int e = 32; e < n_excl; ++e) {
+                        const unsigned int x = C.excl_ent[eb + e];
+                        if ((int)(x & ~kFlag14) == oj) {
+                            if (x & kFlag14) f14 = true; else on = false;
                         }
                     }
                 }
-            }
-            __syncwarp();
-            rows[lane] = make_int2(jb, je);
-            if (n_excl > 0) excl[lane] = lane < n_excl ? C.excl_ent[eb + lane] : 0xffffffffu;
-            __syncwarp();
-        }
-
-        double gix = 0, giy = 0, giz = 0, ev = 0, ee = 0;
-        unsigned int n_eval = 0, n_cand = 0;
-        unsigned int q_head = 0, q_tail = 0;       // ring indices (monotonic; entries at index & (kQueue-1))
-
-        // ---- heavy stage: the 32 (or, at the end, fewer) oldest queue entries, lane l taking entry l
-        auto process = [&](int m) {
-            const bool active = lane < m;
-            const int j = active ? (int)queue[(q_head + lane) & (kQueue - 1)] : i;
-            q_head += m;
-            const double2 pj_xy = sxy[j], pj_zq = szq[j];
-            const int tj = stype[j];
-            const double dx = pi_xy.x - pj_xy.x, dy = pi_xy.y - pj_xy.y, dz = pi_zq.x - pj_zq.x;
-            // strict double, left-to-right, no FMA: Point3d.distance squared
-            const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-            bool on = active && !(r2 > S.r2_max);
-            bool f14 = false;
-            bool counted = on && j > i;            // each unordered pair is counted from its lower sorted index
-            int oj = 0;
-            if (EMIT) oj = orig[j];
-            if (n_excl > 0) {                       // warp-uniform: the list belongs to atom i
-                if (!EMIT) oj = orig[j];
-                const int n_sm = min(n_excl, 32);
-                for (int e = 0; e < n_sm; ++e) {
-                    const unsigned int x = excl[e];
-                    if ((int)(x & ~kFlag14) == oj) {
-                        if (x & kFlag14) f14 = true; else on = false;
+                const bool counted = on && jc > i;    // each unordered pair is counted from its lower sorted index
+                n_eval += __popc(__ballot_sync(0xffffffffu, counted));
+                if (EMIT) {
+                    if (counted) {
+                        const unsigned long long p = atomicAdd(P.cursor, 1ull);
+                        if ((long long)p < P.capacity) { P.out_i[p] = min(oi, oj); P.out_j[p] = max(oi, oj); P.out_14[p] = f14; }
+                    }
+                } else {
+                    double qq2 = qi2 * pj_zq.y;
+                    if (f14) qq2 *= kEle14;
+                    // coincident atoms: keep the (finite) buffered energy, no gradient direction exists
+                    double e1, e2, f;
+                    pair_terms<GRAD>(on ? clamp_r2(r2) : 1.0, trow[tj], qq2, e1, e2, f);
+                    ev += on ? e1 : 0.0;
+                    ee += on ? e2 : 0.0;
+                    if (GRAD) {
+                        f = on ? f : 0.0;
+                        gix = fma(f, dx, gix);
+                        giy = fma(f, dy, giy);
+                        giz = fma(f, dz, giz);
                     }
                 }
-                for (int e = 32; e < n_excl; ++e) {
-                    const unsigned int x = C.excl_ent[eb + e];
-                    if ((int)(x & ~kFlag14) == oj) {
-                        if (x & kFlag14) f14 = true; else on = false;
-                    }
-                }
-                counted = on && j > i;
-            }
-            n_eval += __popc(__ballot_sync(0xffffffffu, counted));
-            if (EMIT) {
-                if (counted) {
-                    const unsigned long long p = atomicAdd(P.cursor, 1ull);
-                    if ((long long)p < P.capacity) { P.out_i[p] = min(oi, oj); P.out_j[p] = max(oi, oj); P.out_14[p] = f14; }
-                }
-            } else {
-                double qq2 = qi2 * pj_zq.y;
-                if (f14) qq2 *= kEle14;
-                // coincident atoms: keep the (finite) buffered energy, no gradient direction exists
-                double e1, e2, f;
-                pair_terms<GRAD>(on ? clamp_r2(r2) : 1.0, trow[tj], qq2, e1, e2, f);
-                ev += on ? e1 : 0.0;
-                ee += on ? e2 : 0.0;
-                if (GRAD) {
-                    f = on ? f : 0.0;
-                    gix = fma(f, dx, gix);
-                    giy = fma(f, dy, giy);
-                    giz = fma(f, dz, giz);
-                }
-            }
-        };
-
-        // ---- candidate scan: trips of 64 candidates (two loads in flight) over the culled row ranges
-        for (int r = 0; r < n_rows; ++r) {
-            const int2 rg = rows[r];
-            for (int base = rg.x; base < rg.y; base += 64) {
-                const int j0 = base + lane, j1 = j0 + 32;
-                const float4 a0 = fxyz[min(j0, rg.y - 1)];
-                const float4 a1 = fxyz[min(j1, rg.y - 1)];
-                const float x0 = fi.x - a0.x, y0 = fi.y - a0.y, z0 = fi.z - a0.z;
-                const float x1 = fi.x - a1.x, y1 = fi.y - a1.y, z1 = fi.z - a1.z;
-                const bool h0 = (x0 * x0 + y0 * y0 + z0 * z0) <= g.r2f_max && j0 < rg.y && j0 != i;
-                const bool h1 = (x1 * x1 + y1 * y1 + z1 * z1) <= g.r2f_max && j1 < rg.y && j1 != i;
-                const unsigned int m0 = __ballot_sync(0xffffffffu, h0);
-                const unsigned int m1 = __ballot_sync(0xffffffffu, h1);
-                if ((m0 | m1) == 0) continue;
-                const int c0n = __popc(m0);
-                if (h0) queue[(q_tail + __popc(m0 & lt_mask)) & (kQueue - 1)] = (unsigned int)j0;
-                if (h1) queue[(q_tail + c0n + __popc(m1 & lt_mask)) & (kQueue - 1)] = (unsigned int)j1;
-                q_tail += c0n + __popc(m1);
-                n_cand += c0n + __popc(m1);
-                __syncwarp();
-                while (q_tail - q_head >= 32) process(32);
             }
         }
-        if (q_tail != q_head) process((int)(q_tail - q_head));
-        __syncwarp();
-
+        n_eval_w += n_eval;
+        n_cand_w += n_hits;
         if (GRAD && !EMIT) {
             gix = warp_sum(gix);
             giy = warp_sum(giy);
@@ -429,18 +518,15 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
                 P.grad[2 * (size_t)S.n_pad + oi] = giz;
             }
         }
-        ev_w += ev;
-        ee_w += ee;
-        n_eval_w += n_eval;
-        n_cand_w += n_cand;
+      }
     }
     if (!EMIT) {
         // energies were accumulated doubled (pair_terms) and every pair was seen from both atoms: x 1/4
-        ev_w = 0.25 * warp_sum(ev_w);
-        ee_w = 0.25 * warp_sum(ee_w);
+        ev = 0.25 * warp_sum(ev);
+        ee = 0.25 * warp_sum(ee);
         if (lane == 0) {
-            P.epart[2 * gw] = ev_w;
-            P.epart[2 * gw + 1] = ee_w;
+            P.epart[2 * gw] = ev;
+            P.epart[2 * gw + 1] = ee;
             P.cpart[2 * gw] = n_eval_w;
             P.cpart[2 * gw + 1] = n_cand_w;
         }
@@ -456,6 +542,11 @@ struct CellPlan {
     int n_epart = 0;
     int grid_pairs = 0;
     int i_begin = 0, i_end = 0, world = 1;
+    unsigned int* d_list = nullptr;
+    int* d_count = nullptr;
+    int* d_overflow = nullptr;
+    int list_cap = 0;
+    int grid_list = 0;
     double cutoff = 0;
     bool built = false;
     bool sorted_valid = false;
@@ -506,9 +597,16 @@ inline int build_cell_plan(CellPlan& p, const HostSystem& hs, const DeviceSystem
         // persistent-style launch: enough warps to fill the chip, grid-stride over atoms
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-        p.grid_pairs = std::max(1, std::min((n + kCellWarps - 1) / kCellWarps, sms * 12));
+        p.grid_pairs = std::max(1, std::min((n + kCellWarps - 1) / kCellWarps, sms * JME_CELL_MIN_BLOCKS));
         p.n_epart = p.grid_pairs * kCellWarps;
         if (!cell_alloc(p, &p.d_epart, 2 * (size_t)p.n_epart, err) || !cell_alloc(p, &p.d_cpart, 2 * (size_t)p.n_epart, err)) return JME_ERR_NOMEM;
+        // survivor lists: fixed capacity per atom (1024 entries; less only if that would exceed 16 GiB)
+        p.list_cap = 1024;
+        while (p.list_cap > 128 && (size_t)n * p.list_cap * sizeof(unsigned int) > ((size_t)16 << 30)) p.list_cap /= 2;
+        if (!cell_alloc(p, &p.d_list, (size_t)std::max(1, n) * p.list_cap, err) || !cell_alloc(p, &p.d_count, n, err) ||
+            !cell_alloc(p, &p.d_overflow, 1, err)) return JME_ERR_NOMEM;
+        cudaMemset(p.d_overflow, 0, sizeof(int));
+        p.grid_list = std::max(1, sms * JME_LIST_MIN_BLOCKS);
         p.built = true;
     }
     cudaMemset(p.d_grad, 0, 3 * (size_t)ds.n_pad * sizeof(double));
@@ -524,7 +622,7 @@ inline int build_cell_plan(CellPlan& p, const HostSystem& hs, const DeviceSystem
 
 inline size_t cells_smem_bytes(const DeviceSystem& ds) {
     return (size_t)ds.n_types * ds.n_types * sizeof(PairConst) +
-           kCellWarps * (kQueue * sizeof(unsigned int) + 32 * sizeof(int2) + 32 * sizeof(unsigned int));
+           kCellWarps * 32 * sizeof(unsigned int);
 }
 
 #define JME_CELL_CHECK()                                                                           \
@@ -556,14 +654,35 @@ inline int run_cell_sort(CellPlan& p, const DeviceSystem& ds, cudaStream_t st, u
     return JME_OK;
 }
 
+// survivor lists for this shard's atoms (after the sort)
+inline int run_cell_lists(CellPlan& p, const DeviceSystem& ds, cudaStream_t st, uint64_t& launches, std::string& err) {
+    if (ds.n == 0) return JME_OK;
+    CellListArgs A{};
+    A.i_begin = p.i_begin; A.i_end = p.i_end;
+    A.list = p.d_list; A.count = p.d_count; A.cap = p.list_cap; A.overflow = p.d_overflow;
+    // about 12 atoms per cell at liquid density: split cells among warps when that leaves resident warps idle
+    const long long resident = (long long)p.grid_list * kListWarps;
+    A.parts = (int)std::max(1ll, std::min(8ll, 2 * resident * 12 / std::max(1, ds.n)));
+    cells_list_kernel<<<p.grid_list, kListThreads, 0, st>>>(p.arr, A);
+    ++launches;
+    JME_CELL_CHECK();
+    return JME_OK;
+}
+
+inline void fill_pair_args(CellPlan& p, CellPairArgs& P) {
+    P.i_begin = p.i_begin; P.i_end = p.i_end;
+    P.list = p.d_list; P.count = p.d_count; P.cap = p.list_cap;
+    // enough warp visits to keep every resident warp busy a few times over
+    const long long resident = (long long)p.grid_pairs * kCellWarps;
+    P.group = (int)std::max(1ll, std::min(32ll, (long long)(p.i_end - p.i_begin) / (resident * 2)));
+    P.grad = p.d_grad; P.epart = p.d_epart; P.cpart = p.d_cpart;
+}
+
 inline int run_cell_path(CellPlan& p, const DeviceSystem& ds, bool grad, cudaStream_t st, uint64_t& launches, std::string& err) {
-    int rc = run_cell_sort(p, ds, st, launches, err);
-    if (rc) return rc;
     if (ds.n == 0) return JME_OK;
     if (grad && p.world > 1) cudaMemsetAsync(p.d_grad, 0, 3 * (size_t)ds.n_pad * sizeof(double), st);
     CellPairArgs P{};
-    P.i_begin = p.i_begin; P.i_end = p.i_end;
-    P.grad = p.d_grad; P.epart = p.d_epart; P.cpart = p.d_cpart;
+    fill_pair_args(p, P);
     const size_t smem = cells_smem_bytes(ds);
     if (grad) {
         auto k = cells_pair_kernel<true, false>;
@@ -583,10 +702,10 @@ inline int run_cell_pairlist(CellPlan& p, const DeviceSystem& ds, int* d_i, int*
                              unsigned long long* d_cursor, cudaStream_t st, uint64_t& launches, std::string& err) {
     int rc = run_cell_sort(p, ds, st, launches, err);
     if (rc) return rc;
+    if ((rc = run_cell_lists(p, ds, st, launches, err))) return rc;
     if (ds.n == 0) return JME_OK;
     CellPairArgs P{};
-    P.i_begin = p.i_begin; P.i_end = p.i_end;
-    P.grad = p.d_grad; P.epart = p.d_epart; P.cpart = p.d_cpart;
+    fill_pair_args(p, P);
     P.out_i = d_i; P.out_j = d_j; P.out_14 = d_f; P.capacity = capacity; P.cursor = d_cursor;
     const size_t smem = cells_smem_bytes(ds);
     auto k = cells_pair_kernel<false, true>;
@@ -595,6 +714,13 @@ inline int run_cell_pairlist(CellPlan& p, const DeviceSystem& ds, int* d_i, int*
     ++launches;
     JME_CELL_CHECK();
     return JME_OK;
+}
+
+// 1 if a survivor list overflowed its capacity in any evaluation so far (results are then incomplete)
+inline int cell_overflowed(CellPlan& p) {
+    int v = 0;
+    if (p.d_overflow) cudaMemcpy(&v, p.d_overflow, sizeof(int), cudaMemcpyDeviceToHost);
+    return v;
 }
 
 }  // namespace jme
