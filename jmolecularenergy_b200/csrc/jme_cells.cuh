@@ -51,6 +51,18 @@ struct GridParams {
     float edge_f, inv_edge_f, cut2_pad_f;   // FP32 copies for the per-row culling (margins included)
 };
 
+struct alignas(32) PosQ { double x, y, z, q; };
+
+// entries of the survivor lists: sorted position of the partner in the low 24 bits, its type index above
+constexpr int kEntryBits = 24;
+constexpr unsigned int kEntryMask = (1u << kEntryBits) - 1u;
+
+__device__ __forceinline__ PosQ load_posq(const PosQ* p) {
+    PosQ r;     // LDG.E.256: one request, one sector
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.q) : "l"(p));
+    return r;
+}
+
 struct CellArrays {
     GridParams* grid;
     int n, n_pad, max_cells;
@@ -62,12 +74,14 @@ struct CellArrays {
     int* order_tmp;          // [n]
     int* orig;               // [n] sorted position -> original atom
     int* scell;              // [n] cell of sorted position
-    double2* sxy;            // [n] sorted x, y   } two 16-byte records per atom: a gather of either touches
-    double2* szq;            // [n] sorted z, q   } half the cache lines a 32-byte record would
-    float4* fxyz;            // [n] sorted positions relative to the grid origin, FP32 (w unused)
-    int* stype;
+    PosQ* spq;               // [n] sorted x, y, z, q: one 32-byte record = one sector, one 256-bit load per gather
+    float4* fxyz;            // [n] sorted positions relative to the grid origin, FP32; w = type index (int bits)
+    int* stype;              // [n] type index by sorted position
+    int* sorted_of;          // [n] original atom -> sorted position
     const long long* excl_ptr;    // CSR over original atom index
-    const unsigned int* excl_ent;
+    const unsigned int* excl_ent; // partners by original index (bit 31 = 1-4 pair)
+    unsigned int* sexcl_ent;      // the same rows with the partners as SORTED positions (rebuilt after every sort)
+    long long n_excl_ent;
     double* bbox_part;       // [blocks][6]
     int bbox_blocks;
 };
@@ -243,10 +257,21 @@ __global__ void cell_rank_gather_kernel(DeviceSystem S, CellArrays C) {
     C.orig[d] = a;
     C.scell[d] = c;
     const double x = S.x[a], y = S.y[a], z = S.z[a];
-    C.sxy[d] = make_double2(x, y);
-    C.szq[d] = make_double2(z, S.q[a]);
-    C.stype[d] = S.type[a];
-    C.fxyz[d] = make_float4((float)(x - g->ox), (float)(y - g->oy), (float)(z - g->oz), 0.0f);
+    PosQ r; r.x = x; r.y = y; r.z = z; r.q = S.q[a];
+    C.spq[d] = r;
+    const int t = S.type[a];
+    C.stype[d] = t;
+    C.sorted_of[a] = d;
+    C.fxyz[d] = make_float4((float)(x - g->ox), (float)(y - g->oy), (float)(z - g->oz), __int_as_float(t));
+}
+
+// exclusion / 1-4 rows with the partners renamed to sorted positions: the evaluation kernel then compares list
+// entries directly, without a gather of the partner's original index
+__global__ void cell_excl_map_kernel(CellArrays C) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= C.n_excl_ent) return;
+    const unsigned int x = C.excl_ent[k];
+    C.sexcl_ent[k] = (unsigned int)C.sorted_of[x & ~kFlag14] | (x & kFlag14);
 }
 
 // ---- 4. pairs ----------------------------------------------------------------------------------
@@ -274,6 +299,10 @@ struct CellPairArgs {
 #ifndef JME_LIST_MIN_BLOCKS
 #define JME_LIST_MIN_BLOCKS 6
 #endif
+#ifndef JME_LIST_K
+#define JME_LIST_K 4
+#endif
+constexpr int kListK = JME_LIST_K;          // candidates per lane per trip (a trip tests 32 * kListK candidates)
 constexpr int kListWarps = JME_LIST_WARPS;
 constexpr int kListThreads = kListWarps * 32;
 
@@ -343,35 +372,49 @@ cells_list_kernel(CellArrays C, CellListArgs P) {
             fis[lane] = fxyz[min(ch + lane, s1 - 1)];
             int my_cnt = 0;                                   // lane il holds the list length of atom ch + il
             __syncwarp();
-            int r0 = 0, r1 = 0;                               // row of this lane's two virtual indices (monotone)
-            for (int vb = 0; vb < total; vb += 64) {
-                const int v0i = vb + lane, v1i = v0i + 32;
-                const bool v0 = v0i < total, v1 = v1i < total;
-                while (r0 < 31 && v0i >= off[r0 + 1]) ++r0;
-                while (r1 < 31 && v1i >= off[r1 + 1]) ++r1;
-                const int j0 = v0 ? jbs[r0] + (v0i - off[r0]) : -1;
-                const int j1 = v1 ? jbs[r1] + (v1i - off[r1]) : -1;
-                float4 a0 = fxyz[max(j0, 0)];
-                float4 a1 = fxyz[max(j1, 0)];
-                if (!v0) a0.x = 1e18f;                        // never passes the distance test
-                if (!v1) a1.x = 1e18f;
+            unsigned int* const rows = P.list + (size_t)ch * P.cap;   // 32-bit offsets from here on
+            int r[kListK];                                    // row of this lane's k-th virtual index (monotone)
+#pragma unroll
+            for (int k = 0; k < kListK; ++k) r[k] = 0;
+            for (int vb = 0; vb < total; vb += 32 * kListK) {
+                float ax[kListK], ay[kListK], az[kListK];
+                unsigned int en[kListK];
+#pragma unroll
+                for (int k = 0; k < kListK; ++k) {
+                    const int vi = vb + 32 * k + lane;
+                    const bool valid = vi < total;
+                    while (r[k] < 31 && vi >= off[r[k] + 1]) ++r[k];
+                    const int j = valid ? jbs[r[k]] + (vi - off[r[k]]) : 0;
+                    const float4 a = fxyz[j];
+                    ax[k] = valid ? a.x : 1e18f;              // never passes the distance test
+                    ay[k] = a.y; az[k] = a.z;
+                    en[k] = (unsigned int)j | ((unsigned int)__float_as_int(a.w) << kEntryBits);
+                }
                 for (int il = 0; il < nc; ++il) {
                     const float4 fi = fis[il];
-                    const float x0 = fi.x - a0.x, y0 = fi.y - a0.y, z0 = fi.z - a0.z;
-                    const float x1 = fi.x - a1.x, y1 = fi.y - a1.y, z1 = fi.z - a1.z;
-                    // the atom itself (distance 0) passes too; the evaluation kernel drops it
-                    const bool h0 = (x0 * x0 + y0 * y0 + z0 * z0) <= g.r2f_max;
-                    const bool h1 = (x1 * x1 + y1 * y1 + z1 * z1) <= g.r2f_max;
-                    const unsigned int m0 = __ballot_sync(0xffffffffu, h0);
-                    const unsigned int m1 = __ballot_sync(0xffffffffu, h1);
-                    if ((m0 | m1) == 0) continue;
+                    bool h[kListK];
+                    unsigned int m[kListK], any = 0;
+#pragma unroll
+                    for (int k = 0; k < kListK; ++k) {
+                        const float x = fi.x - ax[k], y = fi.y - ay[k], z = fi.z - az[k];
+                        // the atom itself (distance 0) passes too; the evaluation kernel drops it
+                        h[k] = (x * x + y * y + z * z) <= g.r2f_max;
+                        m[k] = __ballot_sync(0xffffffffu, h[k]);
+                        any |= m[k];
+                    }
+                    if (any == 0) continue;
                     const int cnt = __shfl_sync(0xffffffffu, my_cnt, il);
-                    const int c0n = __popc(m0), c1n = __popc(m1);
-                    if (cnt + c0n + c1n <= P.cap) {
-                        unsigned int* dst = P.list + (size_t)(ch + il) * P.cap + cnt;
-                        if (h0) __stcs(dst + __popc(m0 & lt_mask), (unsigned int)j0);
-                        if (h1) __stcs(dst + c0n + __popc(m1 & lt_mask), (unsigned int)j1);
-                        if (lane == il) my_cnt += c0n + c1n;
+                    int tot = 0;
+#pragma unroll
+                    for (int k = 0; k < kListK; ++k) tot += __popc(m[k]);
+                    if (cnt + tot <= P.cap) {
+                        unsigned int o = (unsigned int)(il * P.cap + cnt);
+#pragma unroll
+                        for (int k = 0; k < kListK; ++k) {
+                            if (h[k]) __stcs(rows + (o + __popc(m[k] & lt_mask)), en[k]);
+                            o += __popc(m[k]);
+                        }
+                        if (lane == il) my_cnt += tot;
                     } else if (lane == 0) {
                         *P.overflow = 1;
                     }
@@ -388,6 +431,19 @@ cells_list_kernel(CellArrays C, CellListArgs P) {
 // threshold), exclusion / 1-4 lookup, vdW + Coulomb; the gradient of i stays in registers.  Every pair is
 // evaluated from both of its atoms: no scatter, no atomics, deterministic.
 
+constexpr int kExclSmem = 64;     // exclusion entries of the current atom staged per warp
+
+// atoms with more than kExclSmem excluded / 1-4 partners (rare): the rest of the row is read from global
+// memory, out of line so that the hot loop holds no load of its own besides the pipelined ones
+__device__ __noinline__ int excl_tail(const unsigned int* row, int n_excl, int oj) {   // oj: sorted position
+    int hit = 0;                                  // bit 0: excluded, bit 1: 1-4 pair
+    for (int e = kExclSmem; e < n_excl; ++e) {
+        const unsigned int x = row[e];
+        if ((int)(x & ~kFlag14) == oj) hit |= (x & kFlag14) ? 2 : 1;
+    }
+    return hit;
+}
+
 template <bool GRAD, bool EMIT>
 __global__ void __launch_bounds__(kCellThreads, JME_CELL_MIN_BLOCKS)
 cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
@@ -396,16 +452,13 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
     const int TT = S.n_types * S.n_types;
     unsigned int* s_excl = reinterpret_cast<unsigned int*>(s_table + TT);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned int* excl = s_excl + warp * 32;
+    unsigned int* excl = s_excl + warp * kExclSmem;
     for (int t = threadIdx.x; t < TT; t += kCellThreads) s_table[t] = S.table[t];
     __syncthreads();
 
     const int gw = blockIdx.x * kCellWarps + warp;
     const int n_warps = gridDim.x * kCellWarps;
-    const double2* __restrict__ sxy = C.sxy;
-    const double2* __restrict__ szq = C.szq;
-    const int* __restrict__ stype = C.stype;
-    const int* __restrict__ orig = C.orig;
+    const PosQ* __restrict__ spq = C.spq;
 
     double ev = 0, ee = 0;                       // per-lane partial sums over everything this warp does
     unsigned long long n_eval_w = 0, n_cand_w = 0;
@@ -417,11 +470,11 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
     for (int base = P.i_begin + G * gw; base < P.i_end; base += G * n_warps) {
       const int im = min(base + lane, P.i_end - 1);
       const int m_hits = P.count[im];
-      const int m_oi = orig[im];
+      const int m_oi = C.orig[im];
       const long long m_eb = C.excl_ptr[m_oi];
       const int m_nex = (int)(C.excl_ptr[m_oi + 1] - m_eb);
-      const double2 m_xy = sxy[im], m_zq = szq[im];
-      const int m_t = stype[im];
+      const PosQ m_p = spq[im];
+      const int m_t = C.stype[im];
       const int n_here = min(G, P.i_end - base);
       for (int il = 0; il < n_here; ++il) {
         const int i = base + il;
@@ -432,79 +485,86 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
         const int n_excl = __shfl_sync(0xffffffffu, m_nex, il);
         if (n_excl > 0) {
             __syncwarp();
-            excl[lane] = lane < n_excl ? C.excl_ent[eb + lane] : 0xffffffffu;
+            excl[lane] = lane < n_excl ? C.sexcl_ent[eb + lane] : 0xffffffffu;
+            excl[32 + lane] = 32 + lane < n_excl ? C.sexcl_ent[eb + 32 + lane] : 0xffffffffu;
             __syncwarp();
         }
-        double2 pi_xy, pi_zq;
-        pi_xy.x = __shfl_sync(0xffffffffu, m_xy.x, il); pi_xy.y = __shfl_sync(0xffffffffu, m_xy.y, il);
-        pi_zq.x = __shfl_sync(0xffffffffu, m_zq.x, il); pi_zq.y = __shfl_sync(0xffffffffu, m_zq.y, il);
-        const double qi2 = 2.0 * S.ele_scale * pi_zq.y;      // doubled energies, see pair_terms
+        const double pix = __shfl_sync(0xffffffffu, m_p.x, il), piy = __shfl_sync(0xffffffffu, m_p.y, il);
+        const double piz = __shfl_sync(0xffffffffu, m_p.z, il);
+        const double qi2 = 2.0 * S.ele_scale * __shfl_sync(0xffffffffu, m_p.q, il);   // doubled energies, see pair_terms
         const PairConst* trow = s_table + __shfl_sync(0xffffffffu, m_t, il) * S.n_types;
         double gix = 0, giy = 0, giz = 0;
         unsigned int n_eval = 0;
 
-        // software pipeline (issue is in order, so a load has to be issued a whole trip before its first use):
-        // list entries two trips ahead, the atoms they name one trip ahead, arithmetic on the current trip
-        auto entry = [&](int e) { return e < n_hits ? (int)__ldcs(list + e) : i; };
-        int jn = entry(lane), j2 = entry(32 + lane);
-        double2 n_xy = sxy[jn], n_zq = szq[jn];
-        int n_t = stype[jn];
-        for (int b = 0; b < n_hits; b += 32) {
+        // software pipeline.  Issue is in order and a scoreboard wait covers EVERY load outstanding on it, so the
+        // loop is unrolled by two over two register sets (no end-of-trip copies, which would drag the wait for a
+        // trip's own prefetch into that trip): list entries two trips ahead, the atoms they name one trip ahead,
+        // and a trip first consumes its own (old) loads, then issues the next trip's, then does the arithmetic.
+        // Nothing else in a trip takes a scoreboard that could alias the loads': no POPC, no local memory, the
+        // type comes with the list entry and exclusions are compared as sorted positions (no second gather)
+        struct Nb { unsigned int e; PosQ p; };
+        auto entry = [&](int e) { return e < n_hits ? __ldcs(list + e) : (unsigned int)i; };
+        auto gather = [&](Nb& n, unsigned int e) { n.e = e; n.p = load_posq(spq + (e & kEntryMask)); };
+        unsigned int e2 = entry(32 + lane);
+        Nb A, B = {};
+        gather(A, entry(lane));
+        auto trip = [&](const Nb& p, Nb& nx, int b) {
             const bool active = b + lane < n_hits;
-            const int jc = jn, tj = n_t;
-            const double2 pj_xy = n_xy, pj_zq = n_zq;
+            const int jc = (int)(p.e & kEntryMask), tj = (int)(p.e >> kEntryBits);
+            const double qj = p.p.q;
+            const double dx = pix - p.p.x, dy = piy - p.p.y, dz = piz - p.p.z;
+            // strict double, left-to-right, no FMA: Point3d.distance squared
+            const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
             if (b + 32 < n_hits) {
-                jn = j2;                                       // arrived during the previous trip
-                n_xy = sxy[jn]; n_zq = szq[jn]; n_t = stype[jn];
-                j2 = entry(b + 64 + lane);
+                // the address carries a (never taken) dependence on r2, so that these loads are issued after the
+                // wait for this trip's operands and not before it
+                gather(nx, max(e2, (unsigned int)(__double2hiint(r2) >> 31)));
+                e2 = entry(b + 64 + lane);
             }
-            {
-                const double dx = pi_xy.x - pj_xy.x, dy = pi_xy.y - pj_xy.y, dz = pi_zq.x - pj_zq.x;
-                // strict double, left-to-right, no FMA: Point3d.distance squared
-                const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                bool on = active && jc != i && !(r2 > S.r2_max);     // the list holds the atom itself too
-                bool f14 = false;
-                int oj = 0;
-                if (EMIT) oj = orig[jc];
-                if (n_excl > 0) {                      // warp-uniform: the list belongs to atom i
-                    if (!EMIT) oj = orig[jc];
-                    const int n_sm = min(n_excl, 32);
-                    for (int e = 0; e < n_sm; ++e) {
-                        const unsigned int x = excl[e];
-                        if ((int)(x & ~kFlag14) == oj) {
-                            if (x & kFlag14) f14 = true; else on = false;
-                        }
-                    }
-                    for (int e = 32; e < n_excl; ++e) {
-                        const unsigned int x = C.excl_ent[eb + e];
-                        if ((int)(x & ~kFlag14) == oj) {
-                            if (x & kFlag14) f14 = true; else on = false;
-                        }
+            bool on = active && jc != i && !(r2 > S.r2_max);     // the list holds the atom itself too
+            bool f14 = false;
+            if (n_excl > 0) {                      // warp-uniform: the list belongs to atom i
+                const int n_sm = min(n_excl, kExclSmem);
+                for (int e = 0; e < n_sm; ++e) {
+                    const unsigned int x = excl[e];
+                    if ((int)(x & ~kFlag14) == jc) {
+                        if (x & kFlag14) f14 = true; else on = false;
                     }
                 }
-                const bool counted = on && jc > i;    // each unordered pair is counted from its lower sorted index
-                n_eval += __popc(__ballot_sync(0xffffffffu, counted));
-                if (EMIT) {
-                    if (counted) {
-                        const unsigned long long p = atomicAdd(P.cursor, 1ull);
-                        if ((long long)p < P.capacity) { P.out_i[p] = min(oi, oj); P.out_j[p] = max(oi, oj); P.out_14[p] = f14; }
-                    }
-                } else {
-                    double qq2 = qi2 * pj_zq.y;
-                    if (f14) qq2 *= kEle14;
-                    // coincident atoms: keep the (finite) buffered energy, no gradient direction exists
-                    double e1, e2, f;
-                    pair_terms<GRAD>(on ? clamp_r2(r2) : 1.0, trow[tj], qq2, e1, e2, f);
-                    ev += on ? e1 : 0.0;
-                    ee += on ? e2 : 0.0;
-                    if (GRAD) {
-                        f = on ? f : 0.0;
-                        gix = fma(f, dx, gix);
-                        giy = fma(f, dy, giy);
-                        giz = fma(f, dz, giz);
-                    }
+                if (n_excl > kExclSmem) {
+                    const int hit = excl_tail(C.sexcl_ent + eb, n_excl, jc);
+                    if (hit & 1) on = false;
+                    if (hit & 2) f14 = true;
                 }
             }
+            const bool counted = on && jc > i;    // each unordered pair is counted from its lower sorted index
+            n_eval += counted;                    // per lane (POPC would take a scoreboard of its own)
+            if (EMIT) {
+                if (counted) {
+                    const int oj = C.orig[jc];
+                    const unsigned long long q = atomicAdd(P.cursor, 1ull);
+                    if ((long long)q < P.capacity) { P.out_i[q] = min(oi, oj); P.out_j[q] = max(oi, oj); P.out_14[q] = f14; }
+                }
+            } else {
+                double qq2 = qi2 * qj;
+                if (f14) qq2 *= kEle14;
+                // coincident atoms: keep the (finite) buffered energy, no gradient direction exists
+                double e1, e2v, f;
+                pair_terms<GRAD>(on ? clamp_r2(r2) : 1.0, trow[tj], qq2, e1, e2v, f);
+                ev += on ? e1 : 0.0;
+                ee += on ? e2v : 0.0;
+                if (GRAD) {
+                    f = on ? f : 0.0;
+                    gix = fma(f, dx, gix);
+                    giy = fma(f, dy, giy);
+                    giz = fma(f, dz, giz);
+                }
+            }
+        };
+        for (int b = 0; b < n_hits; b += 64) {
+            trip(A, B, b);
+            if (b + 32 >= n_hits) break;
+            trip(B, A, b + 32);
         }
         n_eval_w += n_eval;
         n_cand_w += n_hits;
@@ -524,6 +584,7 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
         // energies were accumulated doubled (pair_terms) and every pair was seen from both atoms: x 1/4
         ev = 0.25 * warp_sum(ev);
         ee = 0.25 * warp_sum(ee);
+        for (int o = 16; o; o >>= 1) n_eval_w += __shfl_xor_sync(0xffffffffu, n_eval_w, o);
         if (lane == 0) {
             P.epart[2 * gw] = ev;
             P.epart[2 * gw + 1] = ee;
@@ -569,6 +630,10 @@ inline bool cell_alloc(CellPlan& p, T** out, size_t count, std::string& err) {
 inline int build_cell_plan(CellPlan& p, const HostSystem& hs, const DeviceSystem& ds, double cutoff, int rank, int world,
                            std::string& err) {
     const int n = ds.n;
+    if ((long long)n > (1ll << kEntryBits) || ds.n_types > 256) {
+        err = "cell path: at most 2^24 atoms and 256 atom types (survivor-list entries are 24 + 8 bits)";
+        return JME_ERR_UNSUPPORTED;
+    }
     if (!p.built) {
         CellArrays& a = p.arr;
         a.n = n; a.n_pad = ds.n_pad;
@@ -578,9 +643,8 @@ inline int build_cell_plan(CellPlan& p, const HostSystem& hs, const DeviceSystem
         bool ok = cell_alloc(p, &a.grid, 1, err) && cell_alloc(p, &a.cell_of, n, err) && cell_alloc(p, &a.count, a.max_cells + 1, err) &&
                   cell_alloc(p, &a.start, a.max_cells + 1, err) && cell_alloc(p, &a.cursor, a.max_cells, err) &&
                   cell_alloc(p, &a.block_sums, scan_blocks, err) && cell_alloc(p, &a.order_tmp, n, err) &&
-                  cell_alloc(p, &a.orig, n, err) && cell_alloc(p, &a.scell, n, err) && cell_alloc(p, &a.sxy, n, err) &&
-                  cell_alloc(p, &a.szq, n, err) && cell_alloc(p, &a.fxyz, n, err) &&
-                  cell_alloc(p, &a.stype, n, err) && cell_alloc(p, &a.bbox_part, 6 * (size_t)a.bbox_blocks, err) &&
+                  cell_alloc(p, &a.orig, n, err) && cell_alloc(p, &a.scell, n, err) && cell_alloc(p, &a.spq, n, err) &&
+                  cell_alloc(p, &a.fxyz, n, err) && cell_alloc(p, &a.stype, n, err) && cell_alloc(p, &a.sorted_of, n, err) && cell_alloc(p, &a.bbox_part, 6 * (size_t)a.bbox_blocks, err) &&
                   cell_alloc(p, &p.d_grad, 3 * (size_t)ds.n_pad, err);
         if (!ok) return JME_ERR_NOMEM;
         long long* d_ptr = nullptr;
@@ -594,6 +658,8 @@ inline int build_cell_plan(CellPlan& p, const HostSystem& hs, const DeviceSystem
             return JME_ERR_CUDA;
         }
         a.excl_ptr = d_ptr; a.excl_ent = d_ent;
+        a.n_excl_ent = (long long)hs.excl_ent.size();
+        if (!cell_alloc(p, &a.sexcl_ent, hs.excl_ent.size(), err)) return JME_ERR_NOMEM;
         // persistent-style launch: enough warps to fill the chip, grid-stride over atoms
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
@@ -622,7 +688,7 @@ inline int build_cell_plan(CellPlan& p, const HostSystem& hs, const DeviceSystem
 
 inline size_t cells_smem_bytes(const DeviceSystem& ds) {
     return (size_t)ds.n_types * ds.n_types * sizeof(PairConst) +
-           kCellWarps * 32 * sizeof(unsigned int);
+           kCellWarps * kExclSmem * sizeof(unsigned int);
 }
 
 #define JME_CELL_CHECK()                                                                           \
@@ -649,6 +715,10 @@ inline int run_cell_sort(CellPlan& p, const DeviceSystem& ds, cudaStream_t st, u
     cell_scatter_kernel<<<nb, 256, 0, st>>>(n, a.cell_of, a.start, a.cursor, a.order_tmp);
     cell_rank_gather_kernel<<<nb, 256, 0, st>>>(ds, a);
     launches += 9;
+    if (a.n_excl_ent > 0) {
+        cell_excl_map_kernel<<<(unsigned int)((a.n_excl_ent + 255) / 256), 256, 0, st>>>(a);
+        ++launches;
+    }
     JME_CELL_CHECK();
     p.sorted_valid = true;
     return JME_OK;
