@@ -32,10 +32,10 @@
 namespace jme {
 
 #ifndef JME_CELL_WARPS
-#define JME_CELL_WARPS 8
+#define JME_CELL_WARPS 4
 #endif
 #ifndef JME_CELL_MIN_BLOCKS
-#define JME_CELL_MIN_BLOCKS 3
+#define JME_CELL_MIN_BLOCKS 5
 #endif
 constexpr int kCellWarps = JME_CELL_WARPS;
 constexpr int kCellThreads = kCellWarps * 32;
@@ -297,7 +297,7 @@ struct CellPairArgs {
 #define JME_LIST_WARPS 8
 #endif
 #ifndef JME_LIST_MIN_BLOCKS
-#define JME_LIST_MIN_BLOCKS 6
+#define JME_LIST_MIN_BLOCKS 4
 #endif
 #ifndef JME_LIST_K
 #define JME_LIST_K 4
