@@ -444,18 +444,46 @@ __device__ __noinline__ int excl_tail(const unsigned int* row, int n_excl, int o
     return hit;
 }
 
+struct alignas(32) GroupAtom { PosQ p; long long eb; int hits, oi, nex, t; int pad[2]; };   // 64 bytes
+constexpr int kChunk = 128;       // list entries per asynchronous copy (one 16-byte piece per lane)
+constexpr int kRingSlots = 3;     // chunk being read + two in flight
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned int s = (unsigned int)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// A warp visits G <= 32 consecutive (cell-sorted) atoms.  Their survivor lists are walked as ONE stream of
+// 32-entry trips (the atom changes inside a trip, warp-uniformly), so the software pipeline never drains:
+//   * list entries travel global -> shared memory by cp.async, two 128-entry chunks ahead of their use and outside
+//     the register scoreboards (a scoreboard wait covers every load outstanding on it, so register loads can only
+//     ever be one trip ahead);
+//   * the partner records (x, y, z, q; one 256-bit load) are gathered one trip ahead into the other of two register
+//     sets (loop unrolled by two: no end-of-trip copies that would drag the wait into the issuing trip), and a trip
+//     first consumes its own operands, then issues the next trip's gather, then does the arithmetic;
+//   * nothing else in a trip takes a long-latency scoreboard: the partner's type comes with the list entry,
+//     exclusions are compared as sorted positions, the next atom's exclusion row is fetched a whole atom ahead.
+// Every pair is evaluated from both of its atoms: the gradient of i stays in registers, no scatter, no atomics.
 template <bool GRAD, bool EMIT>
 __global__ void __launch_bounds__(kCellThreads, JME_CELL_MIN_BLOCKS)
 cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PairConst* s_table = reinterpret_cast<PairConst*>(smem_raw);
     const int TT = S.n_types * S.n_types;
-    unsigned int* s_excl = reinterpret_cast<unsigned int*>(s_table + TT);
+    GroupAtom* s_atoms = reinterpret_cast<GroupAtom*>(s_table + TT);               // 32-byte aligned
+    unsigned int* s_ring = reinterpret_cast<unsigned int*>(s_atoms + kCellWarps * 32);
+    unsigned int* s_excl = s_ring + kCellWarps * kRingSlots * kChunk;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    GroupAtom* atoms = s_atoms + warp * 32;
+    unsigned int* ring = s_ring + warp * kRingSlots * kChunk;
     unsigned int* excl = s_excl + warp * kExclSmem;
     for (int t = threadIdx.x; t < TT; t += kCellThreads) s_table[t] = S.table[t];
     __syncthreads();
 
+    const unsigned int FULL = 0xffffffffu;
     const int gw = blockIdx.x * kCellWarps + warp;
     const int n_warps = gridDim.x * kCellWarps;
     const PosQ* __restrict__ spq = C.spq;
@@ -463,64 +491,115 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
     double ev = 0, ee = 0;                       // per-lane partial sums over everything this warp does
     unsigned long long n_eval_w = 0, n_cand_w = 0;
 
-    // a warp takes 32 consecutive (cell-sorted) atoms at a time: lane l fetches the per-atom data of atom
-    // base + l in one coalesced round, the atoms are then processed one after the other with that data
-    // broadcast by shuffles - no chain of dependent loads at the start of every atom
     const int G = P.group;                      // atoms per warp visit (<= 32): small systems use small groups
     for (int base = P.i_begin + G * gw; base < P.i_end; base += G * n_warps) {
-      const int im = min(base + lane, P.i_end - 1);
-      const int m_hits = P.count[im];
-      const int m_oi = C.orig[im];
-      const long long m_eb = C.excl_ptr[m_oi];
-      const int m_nex = (int)(C.excl_ptr[m_oi + 1] - m_eb);
-      const PosQ m_p = spq[im];
-      const int m_t = C.stype[im];
-      const int n_here = min(G, P.i_end - base);
-      for (int il = 0; il < n_here; ++il) {
-        const int i = base + il;
-        const int n_hits = __shfl_sync(0xffffffffu, m_hits, il);
-        const unsigned int* __restrict__ list = P.list + (size_t)i * P.cap;
-        const int oi = __shfl_sync(0xffffffffu, m_oi, il);
-        const long long eb = __shfl_sync(0xffffffffu, m_eb, il);
-        const int n_excl = __shfl_sync(0xffffffffu, m_nex, il);
-        if (n_excl > 0) {
-            __syncwarp();
-            excl[lane] = lane < n_excl ? C.sexcl_ent[eb + lane] : 0xffffffffu;
-            excl[32 + lane] = 32 + lane < n_excl ? C.sexcl_ent[eb + 32 + lane] : 0xffffffffu;
-            __syncwarp();
+        // lane l fetches the per-atom data of atom base + l in one coalesced round and parks it in shared memory
+        const int n_here = min(G, P.i_end - base);
+        __syncwarp();                            // the previous group's reads of the ring and of atoms[] are over
+        {
+            const int im = min(base + lane, P.i_end - 1);
+            GroupAtom a;
+            a.p = spq[im];
+            a.hits = lane < n_here ? P.count[im] : 0;
+            a.oi = C.orig[im];
+            a.eb = C.excl_ptr[a.oi];
+            a.nex = (int)(C.excl_ptr[a.oi + 1] - a.eb);
+            a.t = C.stype[im];
+            atoms[lane] = a;
         }
-        const double pix = __shfl_sync(0xffffffffu, m_p.x, il), piy = __shfl_sync(0xffffffffu, m_p.y, il);
-        const double piz = __shfl_sync(0xffffffffu, m_p.z, il);
-        const double qi2 = 2.0 * S.ele_scale * __shfl_sync(0xffffffffu, m_p.q, il);   // doubled energies, see pair_terms
-        const PairConst* trow = s_table + __shfl_sync(0xffffffffu, m_t, il) * S.n_types;
+        __syncwarp();
+
+        // chunk requests run over the same (atom, chunk) sequence as the trips, two chunks ahead
+        int q_il = 0, q_c = 0, q_slot = 0;
+        auto request = [&]() {
+            if (q_il < n_here) {
+                const unsigned int* src = P.list + ((size_t)(base + q_il) * P.cap + kChunk * q_c + 4 * lane);
+                cp_async16(ring + q_slot * kChunk + 4 * lane, src);
+                q_slot = q_slot == kRingSlots - 1 ? 0 : q_slot + 1;
+                if (kChunk * (q_c + 1) < atoms[q_il].hits) ++q_c; else { ++q_il; q_c = 0; }
+            }
+            cp_async_commit();                   // an empty group keeps the group count uniform
+        };
+        request(); request(); request();
+        cp_async_wait<2>();                      // chunk 0 has landed (the one exposed latency per group)
+        __syncwarp();
+
+        // current position in the stream and the per-atom state that goes with it
+        int il = 0, b = 0, slot = 0;
+        int n_hits = 0, n_excl = 0, oi = 0, i = base;
+        long long eb = 0;
+        double pix = 0, piy = 0, piz = 0, qi2 = 0;
+        const PairConst* trow = s_table;
         double gix = 0, giy = 0, giz = 0;
         unsigned int n_eval = 0;
+        // exclusion row of the NEXT atom, fetched one atom ahead (first atom: now)
+        unsigned int xe0 = 0xffffffffu, xe1 = 0xffffffffu;
+        auto fetch_excl = [&](int a) {
+            xe0 = xe1 = 0xffffffffu;
+            if (a < n_here) {
+                const long long e0 = atoms[a].eb;
+                const int ne = atoms[a].nex;
+                if (lane < ne) xe0 = C.sexcl_ent[e0 + lane];
+                if (32 + lane < ne) xe1 = C.sexcl_ent[e0 + 32 + lane];
+            }
+        };
+        fetch_excl(0);
 
-        // software pipeline.  Issue is in order and a scoreboard wait covers EVERY load outstanding on it, so the
-        // loop is unrolled by two over two register sets (no end-of-trip copies, which would drag the wait for a
-        // trip's own prefetch into that trip): list entries two trips ahead, the atoms they name one trip ahead,
-        // and a trip first consumes its own (old) loads, then issues the next trip's, then does the arithmetic.
-        // Nothing else in a trip takes a scoreboard that could alias the loads': no POPC, no local memory, the
-        // type comes with the list entry and exclusions are compared as sorted positions (no second gather)
         struct Nb { unsigned int e; PosQ p; };
-        auto entry = [&](int e) { return e < n_hits ? __ldcs(list + e) : (unsigned int)i; };
+#ifdef JME_EXP_NOGATHER
+        auto gather = [&](Nb& n, unsigned int e) { n.e = e; n.p = load_posq(spq + (base + ((e >> 3) & 31))); };
+#else
         auto gather = [&](Nb& n, unsigned int e) { n.e = e; n.p = load_posq(spq + (e & kEntryMask)); };
-        unsigned int e2 = entry(32 + lane);
+#endif
         Nb A, B = {};
-        gather(A, entry(lane));
-        auto trip = [&](const Nb& p, Nb& nx, int b) {
+        {
+            gather(A, lane < atoms[0].hits ? ring[lane] : (unsigned int)base);
+        }
+
+        auto trip = [&](const Nb& p, Nb& nx) -> bool {
+            if (b == 0) {                        // a new atom starts with this trip (warp-uniform)
+                i = base + il;
+                const GroupAtom& a = atoms[il];
+                n_hits = a.hits; oi = a.oi; eb = a.eb; n_excl = a.nex;
+                pix = a.p.x; piy = a.p.y; piz = a.p.z;
+                qi2 = 2.0 * S.ele_scale * a.p.q;                            // doubled energies, see pair_terms
+                trow = s_table + a.t * S.n_types;
+                gix = giy = giz = 0;
+                if (n_excl > 0) {
+                    __syncwarp();
+                    excl[lane] = xe0; excl[32 + lane] = xe1;
+                    __syncwarp();
+                }
+                fetch_excl(il + 1);
+                n_cand_w += n_hits;
+            }
             const bool active = b + lane < n_hits;
             const int jc = (int)(p.e & kEntryMask), tj = (int)(p.e >> kEntryBits);
             const double qj = p.p.q;
             const double dx = pix - p.p.x, dy = piy - p.p.y, dz = piz - p.p.z;
             // strict double, left-to-right, no FMA: Point3d.distance squared
             const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-            if (b + 32 < n_hits) {
-                // the address carries a (never taken) dependence on r2, so that these loads are issued after the
-                // wait for this trip's operands and not before it
-                gather(nx, max(e2, (unsigned int)(__double2hiint(r2) >> 31)));
-                e2 = entry(b + 64 + lane);
+
+            // next position of the stream; entering a chunk = its copy has landed, the slot two behind is reused
+            const bool last = b + 32 >= n_hits;
+            int il2 = il, b2 = b + 32, slot2 = slot;
+            if (last) { il2 = il + 1; b2 = 0; }
+            if (last || (b2 & (kChunk - 1)) == 0) {
+                slot2 = slot == kRingSlots - 1 ? 0 : slot + 1;
+                __syncwarp();                    // every lane is done with the slot about to be overwritten
+                request();
+                cp_async_wait<2>();
+                __syncwarp();
             }
+            if (il2 < n_here) {
+                const int hits2 = last ? atoms[il2].hits : n_hits;
+                unsigned int e = b2 + lane < hits2 ? ring[slot2 * kChunk + (b2 & (kChunk - 1)) + lane] : (unsigned int)base;
+                // the address carries a (never taken) dependence on r2, so that this load is issued after the
+                // wait for this trip's operands and not before it
+                e = max(e, (unsigned int)(__double2hiint(r2) >> 31));
+                gather(nx, e);
+            }
+
             bool on = active && jc != i && !(r2 > S.r2_max);     // the list holds the atom itself too
             bool f14 = false;
             if (n_excl > 0) {                      // warp-uniform: the list belongs to atom i
@@ -550,7 +629,11 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
                 if (f14) qq2 *= kEle14;
                 // coincident atoms: keep the (finite) buffered energy, no gradient direction exists
                 double e1, e2v, f;
+#ifdef JME_EXP_NOMATH
+                { const PairConst pc = trow[tj]; e1 = r2 * pc.k1 + pc.c2; e2v = qq2 * r2 + pc.c3; f = e1 * e2v + pc.c4; }
+#else
                 pair_terms<GRAD>(on ? clamp_r2(r2) : 1.0, trow[tj], qq2, e1, e2v, f);
+#endif
                 ev += on ? e1 : 0.0;
                 ee += on ? e2v : 0.0;
                 if (GRAD) {
@@ -560,31 +643,29 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
                     giz = fma(f, dz, giz);
                 }
             }
+            if (last && GRAD && !EMIT) {           // the atom is complete
+                const double sx = warp_sum(gix), sy = warp_sum(giy), sz = warp_sum(giz);
+                if (lane == 0) {
+                    P.grad[oi] = sx;
+                    P.grad[S.n_pad + oi] = sy;
+                    P.grad[2 * (size_t)S.n_pad + oi] = sz;
+                }
+            }
+            il = il2; b = b2; slot = slot2;
+            return il < n_here;
         };
-        for (int b = 0; b < n_hits; b += 64) {
-            trip(A, B, b);
-            if (b + 32 >= n_hits) break;
-            trip(B, A, b + 32);
+        while (true) {
+            if (!trip(A, B)) break;
+            if (!trip(B, A)) break;
         }
         n_eval_w += n_eval;
-        n_cand_w += n_hits;
-        if (GRAD && !EMIT) {
-            gix = warp_sum(gix);
-            giy = warp_sum(giy);
-            giz = warp_sum(giz);
-            if (lane == 0) {
-                P.grad[oi] = gix;
-                P.grad[S.n_pad + oi] = giy;
-                P.grad[2 * (size_t)S.n_pad + oi] = giz;
-            }
-        }
-      }
+        cp_async_wait<0>();                      // only empty groups can be pending here
     }
     if (!EMIT) {
         // energies were accumulated doubled (pair_terms) and every pair was seen from both atoms: x 1/4
         ev = 0.25 * warp_sum(ev);
         ee = 0.25 * warp_sum(ee);
-        for (int o = 16; o; o >>= 1) n_eval_w += __shfl_xor_sync(0xffffffffu, n_eval_w, o);
+        for (int o = 16; o; o >>= 1) n_eval_w += __shfl_xor_sync(FULL, n_eval_w, o);
         if (lane == 0) {
             P.epart[2 * gw] = ev;
             P.epart[2 * gw + 1] = ee;
@@ -688,7 +769,7 @@ inline int build_cell_plan(CellPlan& p, const HostSystem& hs, const DeviceSystem
 
 inline size_t cells_smem_bytes(const DeviceSystem& ds) {
     return (size_t)ds.n_types * ds.n_types * sizeof(PairConst) +
-           kCellWarps * kExclSmem * sizeof(unsigned int);
+           kCellWarps * (32 * sizeof(GroupAtom) + (kExclSmem + kRingSlots * kChunk) * sizeof(unsigned int));
 }
 
 #define JME_CELL_CHECK()                                                                           \
