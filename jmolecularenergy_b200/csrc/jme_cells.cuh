@@ -35,7 +35,7 @@ namespace jme {
 #define JME_CELL_WARPS 4
 #endif
 #ifndef JME_CELL_MIN_BLOCKS
-#define JME_CELL_MIN_BLOCKS 5
+#define JME_CELL_MIN_BLOCKS 3
 #endif
 constexpr int kCellWarps = JME_CELL_WARPS;
 constexpr int kCellThreads = kCellWarps * 32;
@@ -445,6 +445,11 @@ __device__ __noinline__ int excl_tail(const unsigned int* row, int n_excl, int o
 }
 
 struct alignas(32) GroupAtom { PosQ p; long long eb; int hits, oi, nex, t; int pad[2]; };   // 64 bytes
+#ifndef JME_TRIP_K
+#define JME_TRIP_K 2
+#endif
+constexpr int kTripK = JME_TRIP_K;          // list entries per lane per trip (independent FP64 chains per lane)
+constexpr int kTripSpan = 32 * kTripK;
 constexpr int kChunk = 128;       // list entries per asynchronous copy (one 16-byte piece per lane)
 constexpr int kRingSlots = 3;     // chunk being read + two in flight
 
@@ -545,16 +550,16 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
         };
         fetch_excl(0);
 
-        struct Nb { unsigned int e; PosQ p; };
+        struct Nb { unsigned int e[kTripK]; PosQ p[kTripK]; };
 #ifdef JME_EXP_NOGATHER
-        auto gather = [&](Nb& n, unsigned int e) { n.e = e; n.p = load_posq(spq + (base + ((e >> 3) & 31))); };
+        auto gather = [&](Nb& n, int k, unsigned int e) { n.e[k] = e; n.p[k] = load_posq(spq + (base + ((e >> 3) & 31))); };
 #else
-        auto gather = [&](Nb& n, unsigned int e) { n.e = e; n.p = load_posq(spq + (e & kEntryMask)); };
+        auto gather = [&](Nb& n, int k, unsigned int e) { n.e[k] = e; n.p[k] = load_posq(spq + (e & kEntryMask)); };
 #endif
         Nb A, B = {};
-        {
-            gather(A, lane < atoms[0].hits ? ring[lane] : (unsigned int)base);
-        }
+#pragma unroll
+        for (int k = 0; k < kTripK; ++k)
+            gather(A, k, 32 * k + lane < atoms[0].hits ? ring[32 * k + lane] : (unsigned int)base);
 
         auto trip = [&](const Nb& p, Nb& nx) -> bool {
             if (b == 0) {                        // a new atom starts with this trip (warp-uniform)
@@ -573,16 +578,17 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
                 fetch_excl(il + 1);
                 n_cand_w += n_hits;
             }
-            const bool active = b + lane < n_hits;
-            const int jc = (int)(p.e & kEntryMask), tj = (int)(p.e >> kEntryBits);
-            const double qj = p.p.q;
-            const double dx = pix - p.p.x, dy = piy - p.p.y, dz = piz - p.p.z;
-            // strict double, left-to-right, no FMA: Point3d.distance squared
-            const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            double dx[kTripK], dy[kTripK], dz[kTripK], r2[kTripK];
+#pragma unroll
+            for (int k = 0; k < kTripK; ++k) {
+                dx[k] = pix - p.p[k].x; dy[k] = piy - p.p[k].y; dz[k] = piz - p.p[k].z;
+                // strict double, left-to-right, no FMA: Point3d.distance squared
+                r2[k] = __dadd_rn(__dadd_rn(__dmul_rn(dx[k], dx[k]), __dmul_rn(dy[k], dy[k])), __dmul_rn(dz[k], dz[k]));
+            }
 
             // next position of the stream; entering a chunk = its copy has landed, the slot two behind is reused
-            const bool last = b + 32 >= n_hits;
-            int il2 = il, b2 = b + 32, slot2 = slot;
+            const bool last = b + kTripSpan >= n_hits;
+            int il2 = il, b2 = b + kTripSpan, slot2 = slot;
             if (last) { il2 = il + 1; b2 = 0; }
             if (last || (b2 & (kChunk - 1)) == 0) {
                 slot2 = slot == kRingSlots - 1 ? 0 : slot + 1;
@@ -593,54 +599,79 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
             }
             if (il2 < n_here) {
                 const int hits2 = last ? atoms[il2].hits : n_hits;
-                unsigned int e = b2 + lane < hits2 ? ring[slot2 * kChunk + (b2 & (kChunk - 1)) + lane] : (unsigned int)base;
-                // the address carries a (never taken) dependence on r2, so that this load is issued after the
-                // wait for this trip's operands and not before it
-                e = max(e, (unsigned int)(__double2hiint(r2) >> 31));
-                gather(nx, e);
+                const unsigned int* src = ring + slot2 * kChunk + (b2 & (kChunk - 1)) + lane;
+#pragma unroll
+                for (int k = 0; k < kTripK; ++k) {
+                    unsigned int e = b2 + 32 * k + lane < hits2 ? src[32 * k] : (unsigned int)base;
+                    // the address carries a (never taken) dependence on r2, so that this load is issued after the
+                    // wait for this trip's operands and not before it
+                    e = max(e, (unsigned int)(__double2hiint(r2[k]) >> 31));
+                    gather(nx, k, e);
+                }
             }
 
-            bool on = active && jc != i && !(r2 > S.r2_max);     // the list holds the atom itself too
-            bool f14 = false;
+            // phase 1: which of this lane's pairs count (exact predicate, exclusions, 1-4 flag)
+            bool on[kTripK], f14[kTripK];
+            int tj[kTripK];
+#pragma unroll
+            for (int k = 0; k < kTripK; ++k) {
+                const bool active = b + 32 * k + lane < n_hits;
+                const int jc = (int)(p.e[k] & kEntryMask);
+                tj[k] = (int)(p.e[k] >> kEntryBits);
+                on[k] = active && jc != i && !(r2[k] > S.r2_max);     // the list holds the atom itself too
+                f14[k] = false;
+            }
             if (n_excl > 0) {                      // warp-uniform: the list belongs to atom i
                 const int n_sm = min(n_excl, kExclSmem);
                 for (int e = 0; e < n_sm; ++e) {
                     const unsigned int x = excl[e];
-                    if ((int)(x & ~kFlag14) == jc) {
-                        if (x & kFlag14) f14 = true; else on = false;
+                    const int xj = (int)(x & ~kFlag14);
+#pragma unroll
+                    for (int k = 0; k < kTripK; ++k) {
+                        if (xj == (int)(p.e[k] & kEntryMask)) {
+                            if (x & kFlag14) f14[k] = true; else on[k] = false;
+                        }
                     }
                 }
                 if (n_excl > kExclSmem) {
-                    const int hit = excl_tail(C.sexcl_ent + eb, n_excl, jc);
-                    if (hit & 1) on = false;
-                    if (hit & 2) f14 = true;
+#pragma unroll
+                    for (int k = 0; k < kTripK; ++k) {
+                        const int hit = excl_tail(C.sexcl_ent + eb, n_excl, (int)(p.e[k] & kEntryMask));
+                        if (hit & 1) on[k] = false;
+                        if (hit & 2) f14[k] = true;
+                    }
                 }
             }
-            const bool counted = on && jc > i;    // each unordered pair is counted from its lower sorted index
-            n_eval += counted;                    // per lane (POPC would take a scoreboard of its own)
-            if (EMIT) {
-                if (counted) {
-                    const int oj = C.orig[jc];
-                    const unsigned long long q = atomicAdd(P.cursor, 1ull);
-                    if ((long long)q < P.capacity) { P.out_i[q] = min(oi, oj); P.out_j[q] = max(oi, oj); P.out_14[q] = f14; }
-                }
-            } else {
-                double qq2 = qi2 * qj;
-                if (f14) qq2 *= kEle14;
-                // coincident atoms: keep the (finite) buffered energy, no gradient direction exists
-                double e1, e2v, f;
+            // phase 2: branch-free arithmetic, kTripK independent chains for the scheduler to interleave
+#pragma unroll
+            for (int k = 0; k < kTripK; ++k) {
+                const int jc = (int)(p.e[k] & kEntryMask);
+                const bool counted = on[k] && jc > i;    // each unordered pair is counted from its lower sorted index
+                n_eval += counted;                    // per lane (POPC would take a scoreboard of its own)
+                if (EMIT) {
+                    if (counted) {
+                        const int oj = C.orig[jc];
+                        const unsigned long long q = atomicAdd(P.cursor, 1ull);
+                        if ((long long)q < P.capacity) { P.out_i[q] = min(oi, oj); P.out_j[q] = max(oi, oj); P.out_14[q] = f14[k]; }
+                    }
+                } else {
+                    double qq2 = qi2 * p.p[k].q;
+                    qq2 = f14[k] ? qq2 * kEle14 : qq2;
+                    // coincident atoms: keep the (finite) buffered energy, no gradient direction exists
+                    double e1, e2v, f;
 #ifdef JME_EXP_NOMATH
-                { const PairConst pc = trow[tj]; e1 = r2 * pc.k1 + pc.c2; e2v = qq2 * r2 + pc.c3; f = e1 * e2v + pc.c4; }
+                    { const PairConst pc = trow[tj[k]]; e1 = r2[k] * pc.k1 + pc.c2; e2v = qq2 * r2[k] + pc.c3; f = e1 * e2v + pc.c4; }
 #else
-                pair_terms<GRAD>(on ? clamp_r2(r2) : 1.0, trow[tj], qq2, e1, e2v, f);
+                    pair_terms<GRAD>(on[k] ? clamp_r2(r2[k]) : 1.0, trow[tj[k]], qq2, e1, e2v, f);
 #endif
-                ev += on ? e1 : 0.0;
-                ee += on ? e2v : 0.0;
-                if (GRAD) {
-                    f = on ? f : 0.0;
-                    gix = fma(f, dx, gix);
-                    giy = fma(f, dy, giy);
-                    giz = fma(f, dz, giz);
+                    ev += on[k] ? e1 : 0.0;
+                    ee += on[k] ? e2v : 0.0;
+                    if (GRAD) {
+                        f = on[k] ? f : 0.0;
+                        gix = fma(f, dx[k], gix);
+                        giy = fma(f, dy[k], giy);
+                        giz = fma(f, dz[k], giz);
+                    }
                 }
             }
             if (last && GRAD && !EMIT) {           // the atom is complete
