@@ -32,10 +32,10 @@
 namespace jme {
 
 #ifndef JME_CELL_WARPS
-#define JME_CELL_WARPS 4
+#define JME_CELL_WARPS 8
 #endif
 #ifndef JME_CELL_MIN_BLOCKS
-#define JME_CELL_MIN_BLOCKS 3
+#define JME_CELL_MIN_BLOCKS 2
 #endif
 constexpr int kCellWarps = JME_CELL_WARPS;
 constexpr int kCellThreads = kCellWarps * 32;
@@ -554,7 +554,12 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
 #ifdef JME_EXP_NOGATHER
         auto gather = [&](Nb& n, int k, unsigned int e) { n.e[k] = e; n.p[k] = load_posq(spq + (base + ((e >> 3) & 31))); };
 #else
-        auto gather = [&](Nb& n, int k, unsigned int e) { n.e[k] = e; n.p[k] = load_posq(spq + (e & kEntryMask)); };
+        auto gather = [&](Nb& n, int k, unsigned int e) {
+            n.e[k] = e;
+            unsigned long long addr;              // spq + 32 * index in one IMAD.WIDE.U32
+            asm("mad.wide.u32 %0, %1, 32, %2;" : "=l"(addr) : "r"(e & kEntryMask), "l"(spq));
+            n.p[k] = load_posq(reinterpret_cast<const PosQ*>(addr));
+        };
 #endif
         Nb A, B = {};
 #pragma unroll
@@ -610,64 +615,56 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
                 }
             }
 
-            // phase 1: which of this lane's pairs count (exact predicate, exclusions, 1-4 flag)
-            bool on[kTripK], f14[kTripK];
-            int tj[kTripK];
+            // phase 1: exclusion / 1-4 flags of this lane's partners (bit 0: excluded, bit 1: 1-4 pair)
+            int xf[kTripK];
 #pragma unroll
-            for (int k = 0; k < kTripK; ++k) {
-                const bool active = b + 32 * k + lane < n_hits;
-                const int jc = (int)(p.e[k] & kEntryMask);
-                tj[k] = (int)(p.e[k] >> kEntryBits);
-                on[k] = active && jc != i && !(r2[k] > S.r2_max);     // the list holds the atom itself too
-                f14[k] = false;
-            }
+            for (int k = 0; k < kTripK; ++k) xf[k] = 0;
             if (n_excl > 0) {                      // warp-uniform: the list belongs to atom i
                 const int n_sm = min(n_excl, kExclSmem);
                 for (int e = 0; e < n_sm; ++e) {
                     const unsigned int x = excl[e];
                     const int xj = (int)(x & ~kFlag14);
 #pragma unroll
-                    for (int k = 0; k < kTripK; ++k) {
-                        if (xj == (int)(p.e[k] & kEntryMask)) {
-                            if (x & kFlag14) f14[k] = true; else on[k] = false;
-                        }
-                    }
+                    for (int k = 0; k < kTripK; ++k)
+                        if (xj == (int)(p.e[k] & kEntryMask)) xf[k] |= (x & kFlag14) ? 2 : 1;
                 }
                 if (n_excl > kExclSmem) {
 #pragma unroll
-                    for (int k = 0; k < kTripK; ++k) {
-                        const int hit = excl_tail(C.sexcl_ent + eb, n_excl, (int)(p.e[k] & kEntryMask));
-                        if (hit & 1) on[k] = false;
-                        if (hit & 2) f14[k] = true;
-                    }
+                    for (int k = 0; k < kTripK; ++k) xf[k] |= excl_tail(C.sexcl_ent + eb, n_excl, (int)(p.e[k] & kEntryMask));
                 }
             }
-            // phase 2: branch-free arithmetic, kTripK independent chains for the scheduler to interleave
+            // phase 2: branch-free arithmetic, kTripK independent chains for the scheduler to interleave.  A pair
+            // that does not count (beyond the cutoff, excluded, the atom itself, a padding lane) is evaluated like
+            // the others with its two prefactors multiplied by zero: r2 is clamped away from 0, so every
+            // intermediate is finite and the products are exact zeros - no selects on the results
 #pragma unroll
             for (int k = 0; k < kTripK; ++k) {
-                const int jc = (int)(p.e[k] & kEntryMask);
-                const bool counted = on[k] && jc > i;    // each unordered pair is counted from its lower sorted index
-                n_eval += counted;                    // per lane (POPC would take a scoreboard of its own)
+                const int jc = (int)(p.e[k] & kEntryMask), tj = (int)(p.e[k] >> kEntryBits);
+                // exact predicate: the list holds the atom itself and pairs the FP32 test let through
+                const bool on = b + 32 * k + lane < n_hits && jc != i && !(r2[k] > S.r2_max) && !(xf[k] & 1);
+                if (on && jc > i) ++n_eval;           // each unordered pair is counted from its lower sorted index
                 if (EMIT) {
-                    if (counted) {
+                    if (on && jc > i) {
                         const int oj = C.orig[jc];
                         const unsigned long long q = atomicAdd(P.cursor, 1ull);
-                        if ((long long)q < P.capacity) { P.out_i[q] = min(oi, oj); P.out_j[q] = max(oi, oj); P.out_14[q] = f14[k]; }
+                        if ((long long)q < P.capacity) { P.out_i[q] = min(oi, oj); P.out_j[q] = max(oi, oj); P.out_14[q] = (xf[k] & 2) != 0; }
                     }
                 } else {
-                    double qq2 = qi2 * p.p[k].q;
-                    qq2 = f14[k] ? qq2 * kEle14 : qq2;
-                    // coincident atoms: keep the (finite) buffered energy, no gradient direction exists
+                    // 0, 1 or 0.75 (1-4 pairs) as the high word of a double whose low word is zero
+                    const int hv = on ? 0x3ff00000 : 0;
+                    const int he = on ? ((xf[k] & 2) ? 0x3fe80000 : 0x3ff00000) : 0;
+                    PairConst pc = trow[tj];
+                    pc.k1 *= __hiloint2double(hv, 0);
+                    const double qq2 = (qi2 * p.p[k].q) * __hiloint2double(he, 0);
                     double e1, e2v, f;
 #ifdef JME_EXP_NOMATH
-                    { const PairConst pc = trow[tj[k]]; e1 = r2[k] * pc.k1 + pc.c2; e2v = qq2 * r2[k] + pc.c3; f = e1 * e2v + pc.c4; }
+                    { e1 = r2[k] * pc.k1 + pc.c2; e2v = qq2 * r2[k] + pc.c3; f = e1 * e2v + pc.c4; }
 #else
-                    pair_terms<GRAD>(on[k] ? clamp_r2(r2[k]) : 1.0, trow[tj[k]], qq2, e1, e2v, f);
+                    pair_terms<GRAD>(clamp_r2(r2[k]), pc, qq2, e1, e2v, f);
 #endif
-                    ev += on[k] ? e1 : 0.0;
-                    ee += on[k] ? e2v : 0.0;
+                    ev += e1;
+                    ee += e2v;
                     if (GRAD) {
-                        f = on[k] ? f : 0.0;
                         gix = fma(f, dx[k], gix);
                         giy = fma(f, dy[k], giy);
                         giz = fma(f, dz[k], giz);
