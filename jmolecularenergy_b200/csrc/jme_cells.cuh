@@ -551,16 +551,12 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
         fetch_excl(0);
 
         struct Nb { unsigned int e[kTripK]; PosQ p[kTripK]; };
-#ifdef JME_EXP_NOGATHER
-        auto gather = [&](Nb& n, int k, unsigned int e) { n.e[k] = e; n.p[k] = load_posq(spq + (base + ((e >> 3) & 31))); };
-#else
         auto gather = [&](Nb& n, int k, unsigned int e) {
             n.e[k] = e;
             unsigned long long addr;              // spq + 32 * index in one IMAD.WIDE.U32
             asm("mad.wide.u32 %0, %1, 32, %2;" : "=l"(addr) : "r"(e & kEntryMask), "l"(spq));
             n.p[k] = load_posq(reinterpret_cast<const PosQ*>(addr));
         };
-#endif
         Nb A, B = {};
 #pragma unroll
         for (int k = 0; k < kTripK; ++k)
@@ -657,11 +653,7 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
                     pc.k1 *= __hiloint2double(hv, 0);
                     const double qq2 = (qi2 * p.p[k].q) * __hiloint2double(he, 0);
                     double e1, e2v, f;
-#ifdef JME_EXP_NOMATH
-                    { e1 = r2[k] * pc.k1 + pc.c2; e2v = qq2 * r2[k] + pc.c3; f = e1 * e2v + pc.c4; }
-#else
                     pair_terms<GRAD>(clamp_r2(r2[k]), pc, qq2, e1, e2v, f);
-#endif
                     ev += e1;
                     ee += e2v;
                     if (GRAD) {

@@ -360,3 +360,61 @@ def test_fp64_peak_probe():
     from jmolecularenergy_b200 import measure_fp64_peak
     tflops, mhz = measure_fp64_peak()
     assert 5.0 < tflops < 80.0
+
+
+def _star_in_ion_bath(n_leaves=70, n_side=9):
+    """An artificial hub bonded to ``n_leaves`` atoms inside an ion box: every atom of the star has more than
+    64 excluded partners (hub: its 1-2 partners; leaf: hub + the other leaves as 1-3), which is longer than the
+    exclusion buffer the cell-path pair kernel keeps in shared memory."""
+    from jmolecularenergy_b200 import systems
+    from jmolecularenergy_b200.system import MolecularSystem
+    bath = systems.ion_box(n_side)
+    rng = np.random.default_rng(23)
+    centre = bath.xyz.mean(axis=0)
+    d = rng.normal(size=(n_leaves, 3))
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    star = np.vstack([centre[None, :], centre[None, :] + 1.9 * d])
+    keep = np.linalg.norm(bath.xyz - centre, axis=1) > 3.5
+    xyz = np.vstack([star, bath.xyz[keep]])
+    n_star = n_leaves + 1
+    return MolecularSystem(
+        xyz=xyz, atom_type=np.concatenate([np.full(n_star, 90), bath.atom_type[keep]]),
+        charge=np.concatenate([np.full(n_star, -0.05), bath.charge[keep]]),
+        linear=np.zeros(xyz.shape[0], np.uint8),
+        vdw_type=bath.vdw_type, vdw_alpha=bath.vdw_alpha, vdw_N=bath.vdw_N, vdw_A=bath.vdw_A, vdw_G=bath.vdw_G,
+        vdw_DA=bath.vdw_DA,
+        bond_i=np.zeros(n_leaves, np.int32), bond_j=np.arange(1, n_star, dtype=np.int32),
+        bond_kb=np.full(n_leaves, 3.0, np.float32), bond_r0=np.full(n_leaves, 1.9, np.float32),
+        name=f"star{n_leaves}-in-ions")
+
+
+@pytest.mark.parametrize("path", ["allpairs", "cells"])
+def test_exclusion_rows_longer_than_the_shared_buffer(oracle, path):
+    s = _star_in_ion_bath()
+    ff = gpu_ff(path=path, cutoff=9.0)
+    ff.assignParameters(s)
+    ref = oracle.evaluate(s, cutoff=9.0, gradient=True)
+    assert_parity(ff.calculateComponents(s, gradient=True), ref, f"{path} star")
+    pi, pj, f14 = ff.pairList(s)
+    oi, oj, of = oracle.pair_list(s, cutoff=9.0)
+    assert np.array_equal(pi, oi) and np.array_equal(pj, oj) and np.array_equal(f14, of)
+
+
+def test_cell_path_coincident_atoms_and_long_lists(oracle):
+    """Two ions on the same point (r = 0: finite buffered energy, no gradient direction) and a dense cluster
+    whose survivor lists span several 128-entry chunks, through the cell path."""
+    from jmolecularenergy_b200 import systems
+    s = systems.ion_box(12, spacing=1.7)           # ~2x liquid density: ~850 partners within 10 A
+    s.xyz[701] = s.xyz[64]
+    ff = gpu_ff(path="cells", cutoff=10.0)
+    ff.assignParameters(s)
+    got = ff.calculateComponents(s, gradient=True)
+    ref = oracle.evaluate(s, cutoff=10.0, gradient=True)
+    assert np.isfinite(got["total"]) and np.all(np.isfinite(got["gradient"]))
+    # the CPU restatement divides 0 by 0 for the direction of the coincident pair: compare everything else
+    g_ref = ref.pop("gradient")
+    assert_parity(got, ref, "coincident")
+    ok = np.isfinite(g_ref).all(axis=1)
+    assert ok.sum() >= s.n_atoms - 2
+    floor = 1e-10 * float(np.abs(g_ref[ok]).max())
+    np.testing.assert_allclose(got["gradient"][ok], g_ref[ok], rtol=G_RTOL, atol=floor)
