@@ -179,7 +179,7 @@ def run_reference(args):
             "config": {"workload": args.workload, "description": cfg["desc"], "cutoff": cfg["cutoff"], "sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_opt5k(args):
@@ -219,10 +219,30 @@ def run_opt5k(args):
         line["cpu_baseline"] = {"value": r["pairs"] / cdt, "unit": UNIT, "cores": host_threads(), "kind": "port",
                                 "sample": f"one full energy of {s.name} ({r['pairs']} pairs) in {cdt:.3f} s = {1 / cdt:.1f} calls/s; "
                                           "the reference needs 3N such calls per optimizer step"}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """Keep the real stdout for the ONE JSON line: file descriptor 1 is pointed at stderr for everything else
+    (NCCL prints its version banner on stdout from C code, whatever NCCL_DEBUG says)."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -255,7 +275,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version there)
+        os.environ.pop("NCCL_DEBUG", None)     # no banner; stdout is reserved for the JSON line anyway
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
 
@@ -400,7 +420,7 @@ def main():
         if not args.no_cpu_baseline:
             base, _, _ = cpu_baseline(args.workload, faithful=False)
             line["cpu_baseline"] = base
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
