@@ -159,7 +159,8 @@ uint64_t jme_launch_count(const jme_handle_t* h);
 /* Kernel timing for the roofline: when on, every evaluation records CUDA events (on the launching
  * stream) before the cell build, before and after the nonbonded pair kernel.  jme_profile_read (call it
  * after the stream is synchronised) returns the per-evaluation durations recorded since the last read:
- * nonbonded_ms[k] = pair kernel, build_ms[k] = cell build + sort (0 on the all-pairs path). */
+ * nonbonded_ms[k] = pair kernel (all-pairs tiles, or the FP64 evaluation of the survivor lists),
+ * build_ms[k] = cell sort + survivor-list build of the cutoff path (0 on the all-pairs path). */
 int jme_set_profiling(jme_handle_t* h, int on);
 int jme_profile_read(jme_handle_t* h, float* nonbonded_ms, float* build_ms, int capacity, int* n_read);
 

@@ -6,19 +6,20 @@
 //   1. bounding box (two-stage min/max reduction)              -> grid origin / edge / dims in device memory
 //   2. cell index per atom, per-cell counts (integer atomics)   -> exclusive scan -> cell start offsets
 //   3. scatter to cells, then rank inside each cell by original atom index, so the sorted order (and
-//      with it every later summation order) is deterministic; SoA gather into sorted arrays (FP64
-//      positions/charges, type, and an FP32 copy of the positions relative to the grid origin)
+//      with it every later summation order) is deterministic; gather into sorted arrays (one 32-byte
+//      {x, y, z, q} record per atom, type, an FP32 copy of the positions relative to the grid origin that also
+//      carries the type) and rename the exclusion rows to sorted positions
 //   4a. cells_list_kernel (the neighbour-list build, integer / FP32 only): one warp per CELL scans the 25
 //      neighbour cell rows once for all atoms of the cell - the row ranges are flattened into one virtual index
-//      space so that every trip tests 64 candidates (coalesced FP32 positions relative to the grid origin)
-//      against each atom of the cell with a conservative distance test (padded margins: a superset of the
-//      true pair set) and appends the survivors to that atom's survivor list (fixed capacity, streaming stores).
-//   4b. cells_pair_kernel (FP64): one warp per atom evaluates its list 32 entries at a time with all lanes busy:
-//      exact predicate (bit-identical to the reference's sqrt(dx*dx+dy*dy+dz*dz) > cutoff via the r^2
-//      threshold), exclusion / 1-4 lookup, vdW + Coulomb; list entries are fetched two trips ahead and the
-//      atoms they name one trip ahead (in-order issue: a load must be issued a trip before its first use).
-//      Each pair is evaluated from both of its atoms (no Newton's third law): no scatter, no atomics,
-//      deterministic; energies are halved.
+//      space so that every trip tests 128 candidates (4 per lane, coalesced FP32 positions) against each atom
+//      of the cell with a conservative distance test (padded margins: a superset of the true pair set) and
+//      appends the survivors (sorted position + type, 4 bytes) to that atom's survivor list (fixed capacity,
+//      streaming stores).
+//   4b. cells_pair_kernel (FP64): a warp visits up to 32 consecutive atoms and walks their lists as one stream
+//      of 64-entry trips with all lanes busy: exact predicate (bit-identical to the reference's
+//      sqrt(dx*dx+dy*dy+dz*dz) > cutoff via the r^2 threshold), exclusion / 1-4 lookup, vdW + Coulomb.  See the
+//      comment on the kernel for the software pipeline.  Each pair is evaluated from both of its atoms (no
+//      Newton's third law): no scatter, no atomics, deterministic; energies are halved.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -426,10 +427,6 @@ cells_list_kernel(CellArrays C, CellListArgs P) {
 }
 
 // ---- 4b. evaluation --------------------------------------------------------------------------------
-// One warp per atom i: its survivor list is evaluated 32 entries at a time (all lanes busy):
-// exact FP64 predicate (bit-identical to the reference's sqrt(dx*dx+dy*dy+dz*dz) > cutoff via the r^2
-// threshold), exclusion / 1-4 lookup, vdW + Coulomb; the gradient of i stays in registers.  Every pair is
-// evaluated from both of its atoms: no scatter, no atomics, deterministic.
 
 constexpr int kExclSmem = 64;     // exclusion entries of the current atom staged per warp
 
