@@ -5,8 +5,9 @@
 
 A "step" is one full energy + gradient evaluation of the workload from fresh coordinates: AoS->SoA
 marshalling, (cell build + sort on the cutoff path), nonbonded pair kernel, bonded kernel, final
-reduction and - for N > 1 - the NCCL all-reduce of the packed [energies, gradient] buffer.  Prints ONE JSON
-line on rank 0 (contract in the task description).
+reduction and - for N > 1 - the collectives of owner mode (every rank owns 1/N of the atoms: all-gather of the
+coordinates, all-reduce of the energies, reduce-scatter of the gradient).  Prints ONE JSON line on rank 0
+(contract in the task description).
 
 Default workload: BASELINE.json config 5 ("1M-atom LJ+Coulomb box, atom-row sharded at 1/2/4/8 GPUs"), the
 configuration the metric "pair-interactions/sec at 1/2/4/8 B200" is quoted on; it fits one GPU, so it is the
@@ -15,7 +16,8 @@ N = 1 workload as well (strong scaling: total work fixed as N grows).  --workloa
 
 `value`   : device-resident throughput (coordinates already in HBM), CUDA events on the launching stream.
 `e2e`     : the same metric through the host-buffer C ABI (jme_set_coords + jme_energy_gradient from/to pinned
-            host memory), host wall clock between device synchronisations.
+            host memory), host wall clock between device synchronisations.  For N > 1 every rank copies the
+            coordinate rows of its own atoms in and their gradient rows (+ the energies) out.
 `roofline`: dominant kernel vs the measured FP64 FMA-pipe peak (this path is FP64-bound, not HBM- or
             tensor-bound - BASELINE.md section 3); `roofline_hbm` gives the same kernel against measured HBM.
 """
@@ -291,10 +293,20 @@ def main():
     xyz_dev = torch.from_numpy(system.xyz).to(dev)
     out = ev.new_output(True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    # N > 1: owner mode - a rank supplies the coordinates of the atoms it owns and receives their gradient rows
+    # (all-gather of the coordinates, all-reduce of the 10 energies / counts, reduce-scatter of the gradient)
+    a0, a1 = ev.owned_range()
+    xyz_full, out_full, grad_own = ev.new_owner_buffers()
+    xyz_own_dev = torch.zeros(3 * ev.chunk, dtype=torch.float64, device=dev)
+    xyz_own_dev[:3 * (a1 - a0)] = xyz_dev[a0:a1].reshape(-1)
 
     def step_device():
-        ev.set_coords(xyz_dev)            # AoS -> SoA on the device; invalidates the cell sort
-        ev.evaluate_into(out, True)       # kernels (+ all-reduce) on the current stream
+        if world == 1:
+            ev.set_coords(xyz_dev)            # AoS -> SoA on the device; invalidates the cell sort
+            ev.evaluate_into(out, True)       # kernels on the current stream
+        else:
+            ev.set_coords_owned(xyz_own_dev, xyz_full)
+            ev.evaluate_owned_into(out_full, grad_own)
 
     def barrier():
         if world > 1:
@@ -304,7 +316,7 @@ def main():
     for _ in range(args.warmup):
         step_device()
     barrier()
-    res = unpack(out.cpu().numpy(), n, True)
+    res = unpack((out if world == 1 else out_full).cpu().numpy(), n, False)
     pairs = res["pairs"]
 
     # ---- timed region: K steps, each bracketed by CUDA events on the launching stream, L2 flushed between
@@ -350,6 +362,9 @@ def main():
     #      on the device and copied back, so the host round trip is included on every rank)
     host_xyz = torch.from_numpy(system.xyz.copy()).pin_memory()
     host_out = torch.empty(ev.n_out_grad, dtype=torch.float64).pin_memory()
+    host_own_xyz = torch.zeros(3 * ev.chunk, dtype=torch.float64).pin_memory()
+    host_own_xyz[:3 * (a1 - a0)] = torch.from_numpy(system.xyz[a0:a1].reshape(-1))
+    host_own_out = torch.empty(10 + 3 * ev.chunk, dtype=torch.float64).pin_memory()
     total_e = C.c_double()
     comps = (C.c_double * 7)()
 
@@ -358,9 +373,13 @@ def main():
             st.check(L.jme_set_coords(st.h, host_xyz.data_ptr(), n))
             st.check(L.jme_energy_gradient(st.h, C.byref(total_e), comps, host_out.data_ptr() + 80))
         else:
-            st.check(L.jme_set_coords(st.h, host_xyz.data_ptr(), n))
-            ev.evaluate_into(out, True)
-            host_out.copy_(out, non_blocking=True)
+            # pinned host rows of the owned atoms -> device, all-gather over NVLink, evaluation, reduction,
+            # energies + owned gradient rows -> pinned host
+            xyz_own_dev.copy_(host_own_xyz, non_blocking=True)
+            ev.set_coords_owned(xyz_own_dev, xyz_full)
+            ev.evaluate_owned_into(out_full, grad_own)
+            host_own_out[:10].copy_(out_full[:10], non_blocking=True)
+            host_own_out[10:].copy_(grad_own, non_blocking=True)
             torch.cuda.synchronize()
 
     e2e_steps = max(5, min(args.steps, 30))
@@ -398,10 +417,12 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "description": cfg["desc"], "atoms": n, "pairs_per_step": pairs,
-                       "cutoff": cfg["cutoff"], "path": cfg["path"], "parallelism": f"atom-row shards x{world} + all-reduce" if world > 1 else "single GPU",
+                       "cutoff": cfg["cutoff"], "path": cfg["path"], "parallelism": (f"atom-row shards x{world}; all-gather of coordinates, all-reduce of energies, "
+                                       f"reduce-scatter of the gradient (every rank ends with the rows of its own atoms)")
+                       if world > 1 else "single GPU",
                        "l2": "256 MiB written between timed steps (L2 flush); step = marshal + cell build + pairs + bonded + reduce"},
-            "e2e": {"value": pairs / (e2e_s / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": 24 * n,
-                    "d2h_bytes_per_step": 24 * n + 80, "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps},
+            "e2e": {"value": pairs / (e2e_s / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": 24 * ev.chunk * world,
+                    "d2h_bytes_per_step": (24 * ev.chunk + 80) * world, "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_tflops, "unit": "TFLOP/s",

@@ -441,7 +441,8 @@ int enqueue_launches(jme_handle* h, bool grad, double* d_out_user, bool fork) {
     A.want_grad = grad ? 1 : 0;
     A.out = d_out_user ? d_out_user : h->d_out;
     A.out_host = d_out_user ? nullptr : h->h_out_dev;
-    const int grid = grad ? (h->ds.n + 31) / 32 + 1 : 1;
+    const int apb = A.n_slots == 0 ? kReduceWarps * 32 : 32;      // atoms per block, see reduce_kernel
+    const int grid = grad ? (h->ds.n + apb - 1) / apb + 1 : 1;
     reduce_kernel<<<grid, kReduceWarps * 32, 0, h->stream>>>(A);
     ++h->launches;
     JME_CUDA(h, cudaGetLastError());

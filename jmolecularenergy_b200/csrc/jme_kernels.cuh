@@ -512,10 +512,36 @@ __device__ __forceinline__ double convert_unit(double v, double num, double den)
 __global__ void __launch_bounds__(kReduceWarps * 32)
 reduce_kernel(ReduceArgs A) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_atom_blocks = (A.n + 31) / 32;
+    // no partial-gradient slots (cell path): one atom per THREAD; otherwise 32 atoms per block, warps over slots
+    const int atoms_per_block = A.n_slots == 0 ? kReduceWarps * 32 : 32;
+    const int n_atom_blocks = (A.n + atoms_per_block - 1) / atoms_per_block;
     __shared__ double s_g[kReduceWarps][3][32];
     // energy-only launches have a single block: the energy block
     const int bid = blockIdx.x + (A.want_grad ? 0 : n_atom_blocks);
+    if (bid < n_atom_blocks && A.n_slots == 0) {
+        const int a = bid * atoms_per_block + (int)threadIdx.x;
+        if (a < A.n) {
+            double gx = 0, gy = 0, gz = 0;
+            if (A.direct) {
+                gx = A.direct[a];
+                gy = A.direct[A.n_pad + a];
+                gz = A.direct[2 * (size_t)A.n_pad + a];
+            }
+            for (long long e = A.slot_ptr[a]; e < A.slot_ptr[a + 1]; ++e) {
+                const long long s = A.slot_idx[e];
+                if (s >= A.slot_lo && s < A.slot_hi) {
+                    gx += A.slots[3 * s];
+                    gy += A.slots[3 * s + 1];
+                    gz += A.slots[3 * s + 2];
+                }
+            }
+            double* o = A.out + kOutHeader + 3 * (size_t)a;
+            o[0] = convert_unit(gx, A.unit_num, A.unit_den);
+            o[1] = convert_unit(gy, A.unit_num, A.unit_den);
+            o[2] = convert_unit(gz, A.unit_num, A.unit_den);
+        }
+        return;
+    }
     if (bid < n_atom_blocks) {
         const int a = bid * 32 + lane;
         double gx = 0, gy = 0, gz = 0;

@@ -1,4 +1,4 @@
-"""Multi-GPU evaluation: one process per GPU, atom-row sharding, one all-reduce.
+"""Multi-GPU evaluation: one process per GPU, atom-row sharding, one reduction.
 
 Every rank holds the whole system (coordinates, charges, types, pair table: 36 MB at 10^6 atoms) and
 evaluates its share of the nonbonded rows and bonded terms (``jme_set_shard``); the partial results are
@@ -9,6 +9,11 @@ streams and the process group.
 
 ``local_eval`` can be injected so that the rank bookkeeping and the reduction are testable on CPU with the
 ``gloo`` backend (tests/test_distributed_gloo.py), where no CUDA library call is possible.
+
+Two result layouts: replicated (``evaluate_into``: every rank ends with everything, one all-reduce of 24 N + 80
+bytes) and owner mode (``set_coords_owned`` / ``evaluate_owned_into``: a rank supplies and receives only the rows of
+the atoms it owns - all-gather of the coordinates, all-reduce of the 10-double header, reduce-scatter of the
+gradient).  bench.py uses owner mode for N > 1.
 """
 from __future__ import annotations
 
@@ -106,6 +111,58 @@ class ShardedMMFF94:
             st.check(self.L.jme_eval_device(st.h, 1 if gradient else 0, C.c_void_p(out.data_ptr())))
         if self.world > 1:
             self.dist.all_reduce(out, op=self.dist.ReduceOp.SUM)
+
+    # ---- owner mode: every rank owns a contiguous range of atoms (by original index) ---------------------
+    # Inputs: a rank supplies only the coordinates of its own atoms; one all-gather over NVLink gives every rank
+    # the whole geometry (the cell build needs it).  Outputs: the energies are all-reduced (10 doubles), the
+    # gradient is reduce-scattered, so a rank ends with the gradient rows of the atoms it owns.  Per rank this
+    # moves 1/world of the bytes of the replicated mode over PCIe and half the bytes over NVLink.
+    @property
+    def chunk(self) -> int:
+        """Atoms per rank in owner mode (the last ranks' chunks are padded)."""
+        return (self.n + self.world - 1) // self.world
+
+    def owned_range(self):
+        a0 = min(self.n, self.rank * self.chunk)
+        return a0, min(self.n, a0 + self.chunk)
+
+    def new_owner_buffers(self):
+        """(xyz_full, out_full, grad_own): padded device buffers for ``set_coords_owned`` / ``evaluate_owned_into``."""
+        t, c, w = self.torch, self.chunk, self.world
+        xyz_full = t.zeros(3 * c * w, dtype=t.float64, device=self.device)
+        out_full = t.zeros(OUT_HEADER + 3 * c * w, dtype=t.float64, device=self.device)
+        grad_own = t.zeros(3 * c, dtype=t.float64, device=self.device)
+        return xyz_full, out_full, grad_own
+
+    def set_coords_owned(self, xyz_own, xyz_full) -> None:
+        """``xyz_own``: float64 tensor with the 3 * chunk coordinates of this rank's atoms (padding ignored),
+        on this rank's device.  Gathers everybody's slice into ``xyz_full`` and hands it to the library."""
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(xyz_full, xyz_own)
+        else:
+            xyz_full.copy_(xyz_own)
+        self.set_coords(xyz_full[:3 * self.n].view(self.n, 3))
+
+    def evaluate_owned_into(self, out_full, grad_own) -> None:
+        """Local evaluation into ``out_full``; afterwards ``out_full[:10]`` holds the job-wide energies / pair
+        counts on every rank and ``grad_own`` the gradient rows of this rank's atoms.  No host sync."""
+        n_out = self.n_out_grad
+        if self.local_eval is not None:
+            part = self.local_eval(self.system, self._xyz_host, self.rank, self.world, True)
+            out_full[:n_out].copy_(self.torch.from_numpy(np.ascontiguousarray(part, dtype=np.float64)))
+        else:
+            st = self.state
+            st.check(self.L.jme_eval_device(st.h, 1, C.c_void_p(out_full.data_ptr())))
+        grad_full = out_full[OUT_HEADER:]
+        if self.world > 1:
+            self.dist.all_reduce(out_full[:OUT_HEADER], op=self.dist.ReduceOp.SUM)
+            if out_full.is_cuda:
+                self.dist.reduce_scatter_tensor(grad_own, grad_full, op=self.dist.ReduceOp.SUM)
+            else:                       # gloo has no reduce-scatter: reduce everything, keep the own rows
+                self.dist.all_reduce(grad_full, op=self.dist.ReduceOp.SUM)
+                grad_own.copy_(grad_full[3 * self.chunk * self.rank:3 * self.chunk * (self.rank + 1)])
+        else:
+            grad_own.copy_(grad_full)
 
     def evaluate(self, gradient: bool = True) -> Dict[str, object]:
         out = self.new_output(gradient)

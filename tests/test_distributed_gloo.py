@@ -64,7 +64,15 @@ def _worker(rank, world, port, q):
         assert (ev.rank, ev.world) == (rank, world)
         ev.set_coords(s.xyz)
         res = ev.evaluate(gradient=True)
-        q.put((rank, res["total"], res["vdw"], res["ele"], res["pairs"], res["gradient"]))
+        # owner mode: supply only the own coordinate rows, receive only the own gradient rows
+        xyz_full, out_full, grad_own = ev.new_owner_buffers()
+        a0, a1 = ev.owned_range()
+        own = torch.zeros(3 * ev.chunk, dtype=torch.float64)
+        own[:3 * (a1 - a0)] = torch.from_numpy(s.xyz[a0:a1].reshape(-1))
+        ev.set_coords_owned(own, xyz_full)
+        ev.evaluate_owned_into(out_full, grad_own)
+        owner = (a0, a1, float(out_full[0]), int(round(float(out_full[8]))), grad_own[:3 * (a1 - a0)].numpy().reshape(-1, 3).copy())
+        q.put((rank, res["total"], res["vdw"], res["ele"], res["pairs"], res["gradient"], owner))
     finally:
         dist.destroy_process_group()
 
@@ -83,13 +91,19 @@ def test_two_rank_all_reduce_matches_single_process(oracle):
         assert p.exitcode == 0
     s = systems.water_box(9)
     ref = oracle.evaluate(s, gradient=True)
-    for rank, total, vdw, ele, pairs, grad in got:
+    covered = np.zeros(s.n_atoms, bool)
+    for rank, total, vdw, ele, pairs, grad, (a0, a1, o_total, o_pairs, o_grad) in got:
+        assert o_total == pytest.approx(ref["total"], rel=1e-11) and o_pairs == ref["pairs"]
+        np.testing.assert_allclose(o_grad, ref["gradient"][a0:a1], rtol=1e-11, atol=1e-12)
+        assert not covered[a0:a1].any()
+        covered[a0:a1] = True
         assert total == pytest.approx(ref["total"], rel=1e-11)
         assert vdw == pytest.approx(ref["vdw"], rel=1e-11)
         assert ele == pytest.approx(ref["ele"], rel=1e-11)
         assert pairs == ref["pairs"]
         np.testing.assert_allclose(grad, ref["gradient"], rtol=1e-11, atol=1e-12)
     assert got[0][1] == got[1][1]          # every rank holds the same reduced result
+    assert covered.all()                   # owner mode: the ranks' rows tile the atoms exactly once
 
 
 def test_rank_validation():
