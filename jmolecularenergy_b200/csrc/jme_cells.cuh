@@ -85,6 +85,7 @@ struct CellArrays {
     long long n_excl_ent;
     double* bbox_part;       // [blocks][6]
     int bbox_blocks;
+    int* work_ctr;           // [2] dynamic work distribution: next (cell, part) item / next atom group
 };
 
 // ---- 1. bounding box ---------------------------------------------------------------------------
@@ -326,15 +327,19 @@ cells_list_kernel(CellArrays C, CellListArgs P) {
     int* jbs = s_jb[warp];
     int* off = s_off[warp];
     const GridParams g = *C.grid;
-    const int gw = blockIdx.x * kListWarps + warp;
-    const int n_warps = gridDim.x * kListWarps;
     const unsigned int lt_mask = (1u << lane) - 1u;
     const int width = 2 * g.reach + 1;
     const int n_rows = width * width;          // <= 25: reach <= 2 by construction (edge >= cutoff / 2)
     const float4* __restrict__ fxyz = C.fxyz;
 
     // work item = (cell, part): a cell's atoms are split among P.parts warps when there are few cells
-    for (int w = gw; w < g.ncell * P.parts; w += n_warps) {
+    // (cells differ in work: the items are handed out dynamically; a list does not depend on who builds it)
+    const int n_items = g.ncell * P.parts;
+    for (;;) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(C.work_ctr, 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= n_items) break;
         const int c = w / P.parts, part = w % P.parts;
         const int c0 = C.start[c], c1 = C.start[c + 1];
         const int per = (c1 - c0 + P.parts - 1) / P.parts;
@@ -486,15 +491,20 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
     __syncthreads();
 
     const unsigned int FULL = 0xffffffffu;
-    const int gw = blockIdx.x * kCellWarps + warp;
-    const int n_warps = gridDim.x * kCellWarps;
     const PosQ* __restrict__ spq = C.spq;
 
-    double ev = 0, ee = 0;                       // per-lane partial sums over everything this warp does
-    unsigned long long n_eval_w = 0, n_cand_w = 0;
-
-    const int G = P.group;                      // atoms per warp visit (<= 32): small systems use small groups
-    for (int base = P.i_begin + G * gw; base < P.i_end; base += G * n_warps) {
+    // groups of G atoms (<= 32; small systems use small groups) are handed out dynamically; everything a group
+    // produces (its atoms' gradients, its energy / count partials) is written per group, so the result does not
+    // depend on which warp took it
+    const int G = P.group;
+    for (;;) {
+        int grp = 0;
+        if (lane == 0) grp = atomicAdd(C.work_ctr + 1, 1);
+        grp = __shfl_sync(FULL, grp, 0);
+        const int base = P.i_begin + G * grp;
+        if (base >= P.i_end) break;
+        double ev = 0, ee = 0;                   // per-lane partial sums of this group
+        unsigned long long n_cand_w = 0;
         // lane l fetches the per-atom data of atom base + l in one coalesced round and parks it in shared memory
         const int n_here = min(G, P.i_end - base);
         __syncwarp();                            // the previous group's reads of the ring and of atoms[] are over
@@ -675,19 +685,18 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
             if (!trip(A, B)) break;
             if (!trip(B, A)) break;
         }
-        n_eval_w += n_eval;
         cp_async_wait<0>();                      // only empty groups can be pending here
-    }
-    if (!EMIT) {
-        // energies were accumulated doubled (pair_terms) and every pair was seen from both atoms: x 1/4
-        ev = 0.25 * warp_sum(ev);
-        ee = 0.25 * warp_sum(ee);
-        for (int o = 16; o; o >>= 1) n_eval_w += __shfl_xor_sync(FULL, n_eval_w, o);
-        if (lane == 0) {
-            P.epart[2 * gw] = ev;
-            P.epart[2 * gw + 1] = ee;
-            P.cpart[2 * gw] = n_eval_w;
-            P.cpart[2 * gw + 1] = n_cand_w;
+        if (!EMIT) {
+            // energies were accumulated doubled (pair_terms) and every pair was seen from both atoms: x 1/4
+            ev = 0.25 * warp_sum(ev);
+            ee = 0.25 * warp_sum(ee);
+            for (int o = 16; o; o >>= 1) n_eval += __shfl_xor_sync(FULL, n_eval, o);
+            if (lane == 0) {
+                P.epart[2 * (size_t)grp] = ev;
+                P.epart[2 * (size_t)grp + 1] = ee;
+                P.cpart[2 * (size_t)grp] = n_eval;
+                P.cpart[2 * (size_t)grp + 1] = n_cand_w;
+            }
         }
     }
 }
@@ -698,7 +707,7 @@ struct CellPlan {
     double* d_grad = nullptr;
     double* d_epart = nullptr;
     unsigned long long* d_cpart = nullptr;
-    int n_epart = 0;
+    int n_epart = 0, epart_cap = 0;
     int grid_pairs = 0;
     int i_begin = 0, i_end = 0, world = 1;
     unsigned int* d_list = nullptr;
@@ -743,6 +752,7 @@ inline int build_cell_plan(CellPlan& p, const HostSystem& hs, const DeviceSystem
                   cell_alloc(p, &a.block_sums, scan_blocks, err) && cell_alloc(p, &a.order_tmp, n, err) &&
                   cell_alloc(p, &a.orig, n, err) && cell_alloc(p, &a.scell, n, err) && cell_alloc(p, &a.spq, n, err) &&
                   cell_alloc(p, &a.fxyz, n, err) && cell_alloc(p, &a.stype, n, err) && cell_alloc(p, &a.sorted_of, n, err) && cell_alloc(p, &a.bbox_part, 6 * (size_t)a.bbox_blocks, err) &&
+                  cell_alloc(p, &a.work_ctr, 2, err) &&
                   cell_alloc(p, &p.d_grad, 3 * (size_t)ds.n_pad, err);
         if (!ok) return JME_ERR_NOMEM;
         long long* d_ptr = nullptr;
@@ -762,8 +772,9 @@ inline int build_cell_plan(CellPlan& p, const HostSystem& hs, const DeviceSystem
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
         p.grid_pairs = std::max(1, std::min((n + kCellWarps - 1) / kCellWarps, sms * JME_CELL_MIN_BLOCKS));
-        p.n_epart = p.grid_pairs * kCellWarps;
+        p.n_epart = std::max(1, n);           // one energy / count partial per atom group; groups hold >= 1 atom
         if (!cell_alloc(p, &p.d_epart, 2 * (size_t)p.n_epart, err) || !cell_alloc(p, &p.d_cpart, 2 * (size_t)p.n_epart, err)) return JME_ERR_NOMEM;
+        p.epart_cap = p.n_epart;
         // survivor lists: fixed capacity per atom (1024 entries; less only if that would exceed 16 GiB)
         p.list_cap = 1024;
         while (p.list_cap > 128 && (size_t)n * p.list_cap * sizeof(unsigned int) > ((size_t)16 << 30)) p.list_cap /= 2;
@@ -774,8 +785,8 @@ inline int build_cell_plan(CellPlan& p, const HostSystem& hs, const DeviceSystem
         p.built = true;
     }
     cudaMemset(p.d_grad, 0, 3 * (size_t)ds.n_pad * sizeof(double));
-    cudaMemset(p.d_epart, 0, 2 * (size_t)p.n_epart * sizeof(double));
-    cudaMemset(p.d_cpart, 0, 2 * (size_t)p.n_epart * sizeof(unsigned long long));
+    cudaMemset(p.d_epart, 0, 2 * (size_t)p.epart_cap * sizeof(double));
+    cudaMemset(p.d_cpart, 0, 2 * (size_t)p.epart_cap * sizeof(unsigned long long));
     p.cutoff = cutoff;
     p.world = world;
     p.i_begin = (int)((long long)n * rank / world);
@@ -831,6 +842,7 @@ inline int run_cell_lists(CellPlan& p, const DeviceSystem& ds, cudaStream_t st, 
     // about 12 atoms per cell at liquid density: split cells among warps when that leaves resident warps idle
     const long long resident = (long long)p.grid_list * kListWarps;
     A.parts = (int)std::max(1ll, std::min(8ll, 2 * resident * 12 / std::max(1, ds.n)));
+    cudaMemsetAsync(p.arr.work_ctr, 0, sizeof(int), st);
     cells_list_kernel<<<p.grid_list, kListThreads, 0, st>>>(p.arr, A);
     ++launches;
     JME_CELL_CHECK();
@@ -844,6 +856,7 @@ inline void fill_pair_args(CellPlan& p, CellPairArgs& P) {
     const long long resident = (long long)p.grid_pairs * kCellWarps;
     P.group = (int)std::max(1ll, std::min(32ll, (long long)(p.i_end - p.i_begin) / (resident * 2)));
     P.grad = p.d_grad; P.epart = p.d_epart; P.cpart = p.d_cpart;
+    p.n_epart = std::max(1, (p.i_end - p.i_begin + P.group - 1) / P.group);    // partials written: one per group
 }
 
 inline int run_cell_path(CellPlan& p, const DeviceSystem& ds, bool grad, cudaStream_t st, uint64_t& launches, std::string& err) {
@@ -851,6 +864,7 @@ inline int run_cell_path(CellPlan& p, const DeviceSystem& ds, bool grad, cudaStr
     if (grad && p.world > 1) cudaMemsetAsync(p.d_grad, 0, 3 * (size_t)ds.n_pad * sizeof(double), st);
     CellPairArgs P{};
     fill_pair_args(p, P);
+    cudaMemsetAsync(p.arr.work_ctr + 1, 0, sizeof(int), st);
     const size_t smem = cells_smem_bytes(ds);
     if (grad) {
         auto k = cells_pair_kernel<true, false>;
@@ -875,6 +889,7 @@ inline int run_cell_pairlist(CellPlan& p, const DeviceSystem& ds, int* d_i, int*
     CellPairArgs P{};
     fill_pair_args(p, P);
     P.out_i = d_i; P.out_j = d_j; P.out_14 = d_f; P.capacity = capacity; P.cursor = d_cursor;
+    cudaMemsetAsync(p.arr.work_ctr + 1, 0, sizeof(int), st);
     const size_t smem = cells_smem_bytes(ds);
     auto k = cells_pair_kernel<false, true>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
