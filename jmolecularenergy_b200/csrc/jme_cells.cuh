@@ -25,6 +25,7 @@
 #include <cuda_runtime.h>
 
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "jme_host.hpp"
@@ -508,6 +509,7 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
         // lane l fetches the per-atom data of atom base + l in one coalesced round and parks it in shared memory
         const int n_here = min(G, P.i_end - base);
         __syncwarp();                            // the previous group's reads of the ring and of atoms[] are over
+        bool group_excl;
         {
             const int im = min(base + lane, P.i_end - 1);
             GroupAtom a;
@@ -518,6 +520,7 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
             a.nex = (int)(C.excl_ptr[a.oi + 1] - a.eb);
             a.t = C.stype[im];
             atoms[lane] = a;
+            group_excl = __any_sync(FULL, lane < n_here && a.nex > 0);
         }
         __syncwarp();
 
@@ -555,7 +558,7 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
                 if (32 + lane < ne) xe1 = C.sexcl_ent[e0 + 32 + lane];
             }
         };
-        fetch_excl(0);
+        if (group_excl) fetch_excl(0);
 
         struct Nb { unsigned int e[kTripK]; PosQ p[kTripK]; };
         auto gather = [&](Nb& n, int k, unsigned int e) {
@@ -569,21 +572,27 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
         for (int k = 0; k < kTripK; ++k)
             gather(A, k, 32 * k + lane < atoms[0].hits ? ring[32 * k + lane] : (unsigned int)base);
 
-        auto trip = [&](const Nb& p, Nb& nx) -> bool {
+        // the trip body exists twice: groups without any exclusion row (ions, noble gases) run an instance with the
+        // exclusion handling compiled out
+        auto trip = [&](auto has_excl, const Nb& p, Nb& nx) -> bool {
+            constexpr bool kHasExcl = decltype(has_excl)::value;
             if (b == 0) {                        // a new atom starts with this trip (warp-uniform)
                 i = base + il;
                 const GroupAtom& a = atoms[il];
                 n_hits = a.hits; oi = a.oi; eb = a.eb; n_excl = a.nex;
+                if (!kHasExcl) n_excl = 0;
                 pix = a.p.x; piy = a.p.y; piz = a.p.z;
                 qi2 = 2.0 * S.ele_scale * a.p.q;                            // doubled energies, see pair_terms
                 trow = s_table + a.t * S.n_types;
                 gix = giy = giz = 0;
-                if (n_excl > 0) {
-                    __syncwarp();
-                    excl[lane] = xe0; excl[32 + lane] = xe1;
-                    __syncwarp();
+                if (kHasExcl) {
+                    if (n_excl > 0) {
+                        __syncwarp();
+                        excl[lane] = xe0; excl[32 + lane] = xe1;
+                        __syncwarp();
+                    }
+                    fetch_excl(il + 1);
                 }
-                fetch_excl(il + 1);
                 n_cand_w += n_hits;
             }
             double dx[kTripK], dy[kTripK], dz[kTripK], r2[kTripK];
@@ -622,7 +631,7 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
             int xf[kTripK];
 #pragma unroll
             for (int k = 0; k < kTripK; ++k) xf[k] = 0;
-            if (n_excl > 0) {                      // warp-uniform: the list belongs to atom i
+            if (kHasExcl && n_excl > 0) {          // warp-uniform: the list belongs to atom i
                 const int n_sm = min(n_excl, kExclSmem);
                 for (int e = 0; e < n_sm; ++e) {
                     const unsigned int x = excl[e];
@@ -681,9 +690,16 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
             il = il2; b = b2; slot = slot2;
             return il < n_here;
         };
-        while (true) {
-            if (!trip(A, B)) break;
-            if (!trip(B, A)) break;
+        if (group_excl) {
+            while (true) {
+                if (!trip(std::true_type{}, A, B)) break;
+                if (!trip(std::true_type{}, B, A)) break;
+            }
+        } else {
+            while (true) {
+                if (!trip(std::false_type{}, A, B)) break;
+                if (!trip(std::false_type{}, B, A)) break;
+            }
         }
         cp_async_wait<0>();                      // only empty groups can be pending here
         if (!EMIT) {
@@ -854,7 +870,10 @@ inline void fill_pair_args(CellPlan& p, CellPairArgs& P) {
     P.list = p.d_list; P.count = p.d_count; P.cap = p.list_cap;
     // enough warp visits to keep every resident warp busy a few times over
     const long long resident = (long long)p.grid_pairs * kCellWarps;
-    P.group = (int)std::max(1ll, std::min(32ll, (long long)(p.i_end - p.i_begin) / (resident * 2)));
+#ifndef JME_GROUP_MAX
+#define JME_GROUP_MAX 32
+#endif
+    P.group = (int)std::max(1ll, std::min((long long)JME_GROUP_MAX, (long long)(p.i_end - p.i_begin) / (resident * 2)));
     P.grad = p.d_grad; P.epart = p.d_epart; P.cpart = p.d_cpart;
     p.n_epart = std::max(1, (p.i_end - p.i_begin + P.group - 1) / P.group);    // partials written: one per group
 }
