@@ -318,13 +318,28 @@ struct CellListArgs {
     int* overflow;                 // set to 1 if any list had to be truncated
 };
 
+// squared distance of two candidates (a.x / a.y of each argument) from one atom, packed FP32 (sm_100 f32x2)
+__device__ __forceinline__ unsigned long long f2_bits(float2 v) {
+    return ((unsigned long long)__float_as_uint(v.y) << 32) | __float_as_uint(v.x);
+}
+__device__ __forceinline__ float2 dist2_x2(float2 xi, float2 yi, float2 zi, float2 xa, float2 ya, float2 za) {
+    unsigned long long dx, dy, dz, d2;
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(f2_bits(xi)), "l"(f2_bits(xa)));
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(f2_bits(yi)), "l"(f2_bits(ya)));
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(f2_bits(zi)), "l"(f2_bits(za)));
+    asm("mul.f32x2 %0, %1, %2;" : "=l"(d2) : "l"(dx), "l"(dx));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d2) : "l"(dy), "l"(dy), "l"(d2));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d2) : "l"(dz), "l"(dz), "l"(d2));
+    return make_float2(__uint_as_float((unsigned int)d2), __uint_as_float((unsigned int)(d2 >> 32)));
+}
+
 __global__ void __launch_bounds__(kListThreads, JME_LIST_MIN_BLOCKS)
 cells_list_kernel(CellArrays C, CellListArgs P) {
-    __shared__ float4 s_fi[kListWarps][32];
+    __shared__ float2 s_fi[kListWarps][32][4];  // atom il as (x,x) (y,y) (z,z) -: operands of the packed FP32 test
     __shared__ int s_jb[kListWarps][32];        // first candidate of neighbour row r
     __shared__ int s_off[kListWarps][33];       // exclusive prefix of the row lengths (virtual candidate index)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float4* fis = s_fi[warp];
+    float2 (*fis)[4] = s_fi[warp];
     int* jbs = s_jb[warp];
     int* off = s_off[warp];
     const GridParams g = *C.grid;
@@ -376,7 +391,12 @@ cells_list_kernel(CellArrays C, CellListArgs P) {
         for (int ch = s0; ch < s1; ch += 32) {              // at most 32 atoms of the cell at a time
             const int nc = min(32, s1 - ch);
             __syncwarp();
-            fis[lane] = fxyz[min(ch + lane, s1 - 1)];
+            {
+                const float4 f = fxyz[min(ch + lane, s1 - 1)];
+                fis[lane][0] = make_float2(f.x, f.x);
+                fis[lane][1] = make_float2(f.y, f.y);
+                fis[lane][2] = make_float2(f.z, f.z);
+            }
             int my_cnt = 0;                                   // lane il holds the list length of atom ch + il
             __syncwarp();
             unsigned int* const rows = P.list + (size_t)ch * P.cap;   // 32-bit offsets from here on
@@ -384,6 +404,8 @@ cells_list_kernel(CellArrays C, CellListArgs P) {
 #pragma unroll
             for (int k = 0; k < kListK; ++k) r[k] = 0;
             for (int vb = 0; vb < total; vb += 32 * kListK) {
+                // candidates two by two: the distance test runs on packed FP32 pairs (FADD2 / FMUL2 / FFMA2 of
+                // sm_100: per element the same IEEE operations as the scalar sequence mul, fma, fma)
                 float ax[kListK], ay[kListK], az[kListK];
                 unsigned int en[kListK];
 #pragma unroll
@@ -398,16 +420,21 @@ cells_list_kernel(CellArrays C, CellListArgs P) {
                     en[k] = (unsigned int)j | ((unsigned int)__float_as_int(a.w) << kEntryBits);
                 }
                 for (int il = 0; il < nc; ++il) {
-                    const float4 fi = fis[il];
+                    const float4 fxy = *reinterpret_cast<const float4*>(&fis[il][0]);   // (x, x, y, y)
+                    const float2 fzz = fis[il][2];
                     bool h[kListK];
                     unsigned int m[kListK], any = 0;
 #pragma unroll
-                    for (int k = 0; k < kListK; ++k) {
-                        const float x = fi.x - ax[k], y = fi.y - ay[k], z = fi.z - az[k];
+                    for (int k = 0; k < kListK; k += 2) {
+                        const float2 d2 = dist2_x2(make_float2(fxy.x, fxy.y), make_float2(fxy.z, fxy.w), fzz,
+                                                   make_float2(ax[k], ax[k + 1]), make_float2(ay[k], ay[k + 1]),
+                                                   make_float2(az[k], az[k + 1]));
                         // the atom itself (distance 0) passes too; the evaluation kernel drops it
-                        h[k] = (x * x + y * y + z * z) <= g.r2f_max;
+                        h[k] = d2.x <= g.r2f_max;
+                        h[k + 1] = d2.y <= g.r2f_max;
                         m[k] = __ballot_sync(0xffffffffu, h[k]);
-                        any |= m[k];
+                        m[k + 1] = __ballot_sync(0xffffffffu, h[k + 1]);
+                        any |= m[k] | m[k + 1];
                     }
                     if (any == 0) continue;
                     const int cnt = __shfl_sync(0xffffffffu, my_cnt, il);
