@@ -318,6 +318,11 @@ struct CellListArgs {
     int* overflow;                 // set to 1 if any list had to be truncated
 };
 
+__device__ __forceinline__ void st_cs_if(bool pred, unsigned int* addr, unsigned int v) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.cs.u32 [%1], %2;\n\t}"
+                 ::"r"((unsigned int)pred), "l"(addr), "r"(v) : "memory");
+}
+
 // squared distance of two candidates (a.x / a.y of each argument) from one atom, packed FP32 (sm_100 f32x2)
 __device__ __forceinline__ unsigned long long f2_bits(float2 v) {
     return ((unsigned long long)__float_as_uint(v.y) << 32) | __float_as_uint(v.x);
@@ -445,7 +450,8 @@ cells_list_kernel(CellArrays C, CellListArgs P) {
                         unsigned int o = (unsigned int)(il * P.cap + cnt);
 #pragma unroll
                         for (int k = 0; k < kListK; ++k) {
-                            if (h[k]) __stcs(rows + (o + __popc(m[k] & lt_mask)), en[k]);
+                            // predicated streaming store: no divergent branch around every store
+                            st_cs_if(h[k], rows + (o + __popc(m[k] & lt_mask)), en[k]);
                             o += __popc(m[k]);
                         }
                         if (lane == il) my_cnt += tot;
