@@ -318,9 +318,11 @@ struct CellListArgs {
     int* overflow;                 // set to 1 if any list had to be truncated
 };
 
-__device__ __forceinline__ void st_cs_if(bool pred, unsigned int* addr, unsigned int v) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.cs.u32 [%1], %2;\n\t}"
-                 ::"r"((unsigned int)pred), "l"(addr), "r"(v) : "memory");
+// if (pred) base[index] = v, as a predicated streaming store with a single-instruction address
+__device__ __forceinline__ void st_cs_if(bool pred, unsigned long long base, unsigned int index, unsigned int v) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 a;\n\tsetp.ne.u32 p, %0, 0;\n\tmad.wide.u32 a, %1, 4, %2;\n\t"
+                 "@p st.global.cs.u32 [a], %3;\n\t}"
+                 ::"r"((unsigned int)pred), "r"(index), "l"(base), "r"(v) : "memory");
 }
 
 // squared distance of two candidates (a.x / a.y of each argument) from one atom, packed FP32 (sm_100 f32x2)
@@ -404,7 +406,8 @@ cells_list_kernel(CellArrays C, CellListArgs P) {
             }
             int my_cnt = 0;                                   // lane il holds the list length of atom ch + il
             __syncwarp();
-            unsigned int* const rows = P.list + (size_t)ch * P.cap;   // 32-bit offsets from here on
+            unsigned long long rows = reinterpret_cast<unsigned long long>(P.list + (size_t)ch * P.cap);
+            asm volatile("" : "+l"(rows));                    // keep the base in registers: addresses below are one IMAD.WIDE
             int r[kListK];                                    // row of this lane's k-th virtual index (monotone)
 #pragma unroll
             for (int k = 0; k < kListK; ++k) r[k] = 0;
@@ -451,7 +454,7 @@ cells_list_kernel(CellArrays C, CellListArgs P) {
 #pragma unroll
                         for (int k = 0; k < kListK; ++k) {
                             // predicated streaming store: no divergent branch around every store
-                            st_cs_if(h[k], rows + (o + __popc(m[k] & lt_mask)), en[k]);
+                            st_cs_if(h[k], rows, o + __popc(m[k] & lt_mask), en[k]);
                             o += __popc(m[k]);
                         }
                         if (lane == il) my_cnt += tot;
