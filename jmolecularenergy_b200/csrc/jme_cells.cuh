@@ -329,11 +329,12 @@ __device__ __forceinline__ void st_cs_if(bool pred, unsigned long long base, uns
 __device__ __forceinline__ unsigned long long f2_bits(float2 v) {
     return ((unsigned long long)__float_as_uint(v.y) << 32) | __float_as_uint(v.x);
 }
-__device__ __forceinline__ float2 dist2_x2(float2 xi, float2 yi, float2 zi, float2 xa, float2 ya, float2 za) {
+__device__ __forceinline__ float2 dist2_x2(unsigned long long xi, unsigned long long yi, unsigned long long zi,
+                                           unsigned long long xa, unsigned long long ya, unsigned long long za) {
     unsigned long long dx, dy, dz, d2;
-    asm("sub.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(f2_bits(xi)), "l"(f2_bits(xa)));
-    asm("sub.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(f2_bits(yi)), "l"(f2_bits(ya)));
-    asm("sub.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(f2_bits(zi)), "l"(f2_bits(za)));
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(xi), "l"(xa));
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(yi), "l"(ya));
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(zi), "l"(za));
     asm("mul.f32x2 %0, %1, %2;" : "=l"(d2) : "l"(dx), "l"(dx));
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d2) : "l"(dy), "l"(dy), "l"(d2));
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d2) : "l"(dz), "l"(dz), "l"(d2));
@@ -427,6 +428,15 @@ cells_list_kernel(CellArrays C, CellListArgs P) {
                     ay[k] = a.y; az[k] = a.z;
                     en[k] = (unsigned int)j | ((unsigned int)__float_as_int(a.w) << kEntryBits);
                 }
+                // packed once per trip, so that the pairs stay in aligned register pairs through the atom loop
+                unsigned long long px[kListK / 2], py[kListK / 2], pz[kListK / 2];
+#pragma unroll
+                for (int k = 0; k < kListK; k += 2) {
+                    px[k / 2] = f2_bits(make_float2(ax[k], ax[k + 1]));
+                    py[k / 2] = f2_bits(make_float2(ay[k], ay[k + 1]));
+                    pz[k / 2] = f2_bits(make_float2(az[k], az[k + 1]));
+                    asm volatile("" : "+l"(px[k / 2]), "+l"(py[k / 2]), "+l"(pz[k / 2]));
+                }
                 for (int il = 0; il < nc; ++il) {
                     const float4 fxy = *reinterpret_cast<const float4*>(&fis[il][0]);   // (x, x, y, y)
                     const float2 fzz = fis[il][2];
@@ -434,9 +444,8 @@ cells_list_kernel(CellArrays C, CellListArgs P) {
                     unsigned int m[kListK], any = 0;
 #pragma unroll
                     for (int k = 0; k < kListK; k += 2) {
-                        const float2 d2 = dist2_x2(make_float2(fxy.x, fxy.y), make_float2(fxy.z, fxy.w), fzz,
-                                                   make_float2(ax[k], ax[k + 1]), make_float2(ay[k], ay[k + 1]),
-                                                   make_float2(az[k], az[k + 1]));
+                        const float2 d2 = dist2_x2(f2_bits(make_float2(fxy.x, fxy.y)), f2_bits(make_float2(fxy.z, fxy.w)),
+                                                   f2_bits(fzz), px[k / 2], py[k / 2], pz[k / 2]);
                         // the atom itself (distance 0) passes too; the evaluation kernel drops it
                         h[k] = d2.x <= g.r2f_max;
                         h[k + 1] = d2.y <= g.r2f_max;
