@@ -106,6 +106,7 @@ struct jme_handle {
 };
 
 namespace {
+constexpr int kListOverflow = 1;       // internal: finish_host saw the overflow flag of the cell path
 
 #define JME_CUDA(h, call)                                                                        \
     do {                                                                                         \
@@ -428,6 +429,7 @@ int enqueue_launches(jme_handle* h, bool grad, double* d_out_user, bool fork) {
         if (pe) cudaEventRecord(pe[1], h->stream);
         if ((rc = run_cell_path(h->cells, h->ds, grad, h->stream, h->launches, h->err))) return rc;
         A.gpart = nullptr; A.n_slots = 0; A.direct = h->cells.d_grad;
+        A.overflow = h->cells.d_overflow;
         A.epart = h->cells.d_epart; A.cpart = h->cells.d_cpart; A.n_epart = h->cells.n_epart;
     }
     if (pe) { cudaEventRecord(pe[2], h->stream); ++h->prof_used; }
@@ -506,10 +508,46 @@ int finish_host(jme_handle* h, bool grad, double* total, double* comps, double* 
     if (comps) for (int c = 0; c < JME_N_COMPONENTS; ++c) comps[c] = h->h_out[1 + c];
     h->last_pairs = (uint64_t)h->h_out[8];
     h->last_cand = (uint64_t)h->h_out[9];
-    if (h->active_path == JME_PATH_CELLS && cell_overflowed(h->cells))
-        return fail(h, JME_ERR_UNSUPPORTED, "a cutoff sphere holds more atoms than the survivor-list capacity (" +
-                    std::to_string(h->cells.list_cap) + "); the system is too dense for the cell path at this cutoff");
+    if (h->active_path == JME_PATH_CELLS && h->h_out[kOutHeader] != 0.0) return kListOverflow;
     return JME_OK;
+}
+
+// after an overflow: survivor lists with twice the capacity per atom (the old ones are released), flag cleared
+int grow_cell_lists(jme_handle* h) {
+    CellPlan& p = h->cells;
+    const int cap = p.list_cap * 2;
+    const size_t count = (size_t)std::max(1, h->ds.n) * cap;
+    if (cap > (1 << 16)) { h->err = "survivor-list capacity limit"; return JME_ERR_NOMEM; }
+    dev_free(h, p.d_list);
+    p.d_list = nullptr;
+    int rc = dev_alloc(h, &p.d_list, count);
+    if (rc) {            // keep the plan usable at the old capacity
+        std::string why = h->err;
+        if (dev_alloc(h, &p.d_list, count / 2)) { p.built = false; h->plan_dirty = true; }
+        h->err = why;
+        return rc;
+    }
+    p.list_cap = cap;
+    JME_CUDA(h, cudaMemset(p.d_overflow, 0, sizeof(int)));
+    return JME_OK;
+}
+
+// Host-API evaluation on the cell path: when a survivor list overflowed, double the list capacity and evaluate
+// again (dense systems / long cutoffs); gives up when the lists would not fit in memory.
+int eval_host(jme_handle* h, bool grad, double* total, double* comps, double* grad_xyz) {
+    for (;;) {
+        int rc = enqueue_eval(h, grad, nullptr);
+        if (rc) return rc;
+        rc = finish_host(h, grad, total, comps, grad_xyz);
+        if (rc != kListOverflow) return rc;
+        const int old_cap = h->cells.list_cap;
+        if (int g = grow_cell_lists(h)) {
+            if (g == JME_ERR_NOMEM) h->err = "a cutoff sphere holds more atoms than the survivor-list capacity (" +
+                std::to_string(old_cap) + ") and larger lists do not fit in device memory: " + h->err;
+            return g;
+        }
+        ++h->graph_epoch;                  // the list pointers / capacity are baked into the captured graph
+    }
 }
 
 }  // namespace
@@ -568,7 +606,7 @@ int jme_create(const jme_system_t* sys, jme_handle_t** out) {
     if ((rc = dev_upload(h, &h->d_table, table))) return bail(rc);
     if ((rc = dev_alloc(h, &h->d_xyz_stage, 3 * (size_t)std::max(1, n)))) return bail(rc);
     if ((rc = dev_alloc(h, &h->d_out, kOutHeader + 3 * (size_t)std::max(1, n)))) return bail(rc);
-    if (cudaHostAlloc(&h->h_out, kOutHeader * sizeof(double), cudaHostAllocMapped) != cudaSuccess ||
+    if (cudaHostAlloc(&h->h_out, (kOutHeader + 1) * sizeof(double), cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer(&h->h_out_dev, h->h_out, 0) != cudaSuccess) { h->err = "cudaHostAlloc (mapped) failed"; return bail(JME_ERR_CUDA); }
 
     h->ds.n = n; h->ds.n_pad = n_pad; h->ds.n_blocks = n_pad / kTile; h->ds.n_types = std::max(1, hs.n_types);
@@ -696,18 +734,14 @@ int jme_get_coords(jme_handle_t* h, double* xyz, int64_t n_atoms) {
 int jme_energy(jme_handle_t* h, double* total, double comps[JME_N_COMPONENTS]) {
     if (!h) return JME_ERR_INVALID;
     JME_CUDA(h, cudaSetDevice(h->device));
-    int rc = enqueue_eval(h, false, nullptr);
-    if (rc) return rc;
-    return finish_host(h, false, total, comps, nullptr);
+    return eval_host(h, false, total, comps, nullptr);
 }
 
 int jme_energy_gradient(jme_handle_t* h, double* total, double comps[JME_N_COMPONENTS], double* grad_xyz) {
     if (!h) return JME_ERR_INVALID;
     if (!grad_xyz && h->hs.n > 0) return fail(h, JME_ERR_INVALID, "null gradient buffer");
     JME_CUDA(h, cudaSetDevice(h->device));
-    int rc = enqueue_eval(h, true, nullptr);
-    if (rc) return rc;
-    return finish_host(h, true, total, comps, grad_xyz);
+    return eval_host(h, true, total, comps, grad_xyz);
 }
 
 int jme_gd_minimize(jme_handle_t* h, int max_steps, double step_size, double threshold, double* xyz,
@@ -720,9 +754,7 @@ int jme_gd_minimize(jme_handle_t* h, int max_steps, double step_size, double thr
     int64_t calls = 0;
     auto energy = [&](double& e) -> int {
         ++calls;
-        int r = enqueue_eval(h, false, nullptr);
-        if (r) return r;
-        return finish_host(h, false, &e, nullptr, nullptr);
+        return eval_host(h, false, &e, nullptr, nullptr);
     };
     auto move = [&](int64_t a, int i, double d) -> int {          // movePoint, GradientDescentMinimizer.java:107-115
         xyz[3 * a + i] += d;
@@ -815,7 +847,14 @@ int jme_pair_list(jme_handle_t* h, int32_t* pair_i, int32_t* pair_j, uint8_t* is
             ++h->launches;
         }
     } else {
-        rc = run_cell_pairlist(h->cells, h->ds, d_i, d_j, d_f, capacity, d_cur, h->stream, h->launches, h->err);
+        // a truncated survivor list would silently drop pairs: grow the lists and redo, like eval_host
+        for (;;) {
+            rc = run_cell_pairlist(h->cells, h->ds, d_i, d_j, d_f, capacity, d_cur, h->stream, h->launches, h->err);
+            if (rc || cudaStreamSynchronize(h->stream) != cudaSuccess || !cell_overflowed(h->cells)) break;
+            if ((rc = grow_cell_lists(h))) break;
+            ++h->graph_epoch;
+            cudaMemsetAsync(d_cur, 0, sizeof(unsigned long long), h->stream);
+        }
     }
     unsigned long long cnt = 0;
     cudaError_t ce = cudaMemcpyAsync(&cnt, d_cur, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream);

@@ -963,7 +963,7 @@ inline int run_cell_pairlist(CellPlan& p, const DeviceSystem& ds, int* d_i, int*
     return JME_OK;
 }
 
-// 1 if a survivor list overflowed its capacity in any evaluation so far (results are then incomplete)
+// 1 if a survivor list overflowed its capacity since the flag was last cleared (results are then incomplete)
 inline int cell_overflowed(CellPlan& p) {
     int v = 0;
     if (p.d_overflow) cudaMemcpy(&v, p.d_overflow, sizeof(int), cudaMemcpyDeviceToHost);

@@ -501,7 +501,9 @@ struct ReduceArgs {
     double unit_num, unit_den;      // (v * num) / den, ForceField.java:157; both 1 for kcal/mol
     int want_grad;
     double* out;                    // [0] total [1..7] comps [8] pairs evaluated [9] candidates [10..] gradient AoS
-    double* out_host;               // optional: mapped pinned host copy of the 10-double header (zero-copy result)
+    double* out_host;               // optional: mapped pinned host copy of the header (zero-copy result), kOutHeader + 1
+                                    // doubles: [kOutHeader] = overflow flag
+    const int* overflow;            // optional: set when a survivor list of the cell path was truncated
 };
 constexpr int kOutHeader = 10;
 
@@ -616,11 +618,15 @@ reduce_kernel(ReduceArgs A) {
             A.out[1 + c] = v;
             total += v;
         }
-        A.out[0] = total;
+        // a truncated survivor list means missing pairs: the total is poisoned (NaN) so that no caller - host or
+        // device side, before or after an all-reduce - can mistake the result for a valid energy
+        const int ovf = A.overflow ? *A.overflow : 0;
+        A.out[0] = ovf ? __longlong_as_double(0x7ff8000000000000ll) : total;
         A.out[8] = (double)s_c[0][0];
         A.out[9] = (double)s_c[1][0];
         if (A.out_host) {
             for (int c = 0; c < kOutHeader; ++c) A.out_host[c] = A.out[c];
+            A.out_host[kOutHeader] = (double)ovf;
             __threadfence_system();
         }
     }

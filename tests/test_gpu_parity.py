@@ -418,3 +418,24 @@ def test_cell_path_coincident_atoms_and_long_lists(oracle):
     assert ok.sum() >= s.n_atoms - 2
     floor = 1e-10 * float(np.abs(g_ref[ok]).max())
     np.testing.assert_allclose(got["gradient"][ok], g_ref[ok], rtol=G_RTOL, atol=floor)
+
+
+def test_cell_path_grows_its_lists_for_dense_systems(oracle):
+    """More partners inside the cutoff sphere than the initial survivor-list capacity (1024): the host API grows
+    the lists and re-evaluates; a device-side caller of a fresh handle sees a poisoned (NaN) total, never a
+    silently truncated sum."""
+    from jmolecularenergy_b200 import systems
+    from jmolecularenergy_b200.distributed import ShardedMMFF94, unpack
+    s = systems.ion_box(13, spacing=1.7)           # 0.2 atoms/A^3: ~1450 partners within 12 A
+    ev = ShardedMMFF94(s, cutoff=12.0, path="cells", rank=0, world=1)
+    ev.set_coords(s.xyz)
+    raw = ev.evaluate(gradient=True)
+    ev.close()
+    assert np.isnan(raw["total"])
+    ff = gpu_ff(path="cells", cutoff=12.0)
+    ff.assignParameters(s)
+    got = ff.calculateComponents(s, gradient=True)
+    ref = oracle.evaluate(s, cutoff=12.0, gradient=True)
+    assert_parity(got, ref, "dense")
+    pi, pj, f14 = ff.pairList(s)
+    assert len(pi) == ref["pairs"]
