@@ -137,7 +137,11 @@ int jme_pair_list(jme_handle_t* h, int32_t* pair_i, int32_t* pair_j, uint8_t* is
  * JME_STREAM_OWN selects the handle's own non-blocking stream again (the state after jme_create);
  * nothing is synchronised.  d_xyz: device AoS [n_atoms][3].  d_out: device doubles
  * [0]=total [1..7]=components [8]=pairs evaluated [9]=pairs candidate (both as double)
- * [10..10+3n) gradient AoS (only when want_gradient).  This is the buffer a multi-GPU caller all-reduces. */
+ * [10..10+3n) gradient AoS (only when want_gradient).  This is the buffer a multi-GPU caller all-reduces.
+ * Nothing can be returned from an asynchronous call, so a failure of the cutoff path that only the device
+ * sees - a cutoff sphere with more atoms than the survivor-list capacity - sets the total ([0]) to NaN; the
+ * host entry points (jme_energy, jme_energy_gradient, jme_pair_list) grow the lists and re-evaluate instead,
+ * after which the device entry points work at the new capacity too. */
 #define JME_STREAM_OWN ((void*)(intptr_t)-1)
 int jme_set_stream(jme_handle_t* h, void* stream);
 int jme_set_coords_device(jme_handle_t* h, const double* d_xyz, int64_t n_atoms);
