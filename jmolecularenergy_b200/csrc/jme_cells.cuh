@@ -306,6 +306,7 @@ struct CellPairArgs {
 #define JME_LIST_K 4
 #endif
 constexpr int kListK = JME_LIST_K;          // candidates per lane per trip (a trip tests 32 * kListK candidates)
+static_assert(kListK >= 2 && kListK % 2 == 0, "the packed FP32 test takes the candidates two by two");
 constexpr int kListWarps = JME_LIST_WARPS;
 constexpr int kListThreads = kListWarps * 32;
 
@@ -500,6 +501,7 @@ constexpr int kTripK = JME_TRIP_K;          // list entries per lane per trip (i
 constexpr int kTripSpan = 32 * kTripK;
 constexpr int kChunk = 128;       // list entries per asynchronous copy (one 16-byte piece per lane)
 constexpr int kRingSlots = 3;     // chunk being read + two in flight
+static_assert(kChunk % kTripSpan == 0, "a trip must not straddle two chunks");
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     const unsigned int s = (unsigned int)__cvta_generic_to_shared(smem);
