@@ -113,6 +113,13 @@ class MMFFTables:
         self.stbn: List[Tuple[int, int, int, int, np.float32, np.float32]] = [
             (int(float(r[0])), int(float(r[1])), int(float(r[2])), int(float(r[3])), f32(r[4]), f32(r[5]))
             for r in _rows(p("MMFF94-stretch-bend.par"))]
+        # default stretch-bend constants by periodic-table rows (IR, JR, KR) -> (F(I_J,K), F(K_J,I)), used when
+        # the typed table has no row (MMFF94.java:1047-1060)
+        self.stbn_default: Dict[Tuple[int, int, int], Tuple[np.float32, np.float32]] = {}
+        emp = p("MMFF94-stretch-bend-empirical.par")
+        if os.path.exists(emp):
+            for r in _rows(emp):
+                self.stbn_default.setdefault((int(r[0]), int(r[1]), int(r[2])), (f32(r[3]), f32(r[4])))
         oop_file = "MMFF94s-out-of-plane.par" if mmff94s else "MMFF94-out-of-plane.par"
         self.oop: List[Tuple[int, int, int, int, np.float32]] = [
             (int(float(r[0])), int(float(r[1])), int(float(r[2])), int(float(r[3])), f32(r[4]))
@@ -194,7 +201,21 @@ class MMFFTables:
         for row in self.stbn:
             if row[2] == tj and row[0] == sbt and row[1] == ti and row[3] == tk:
                 return (row[5], row[4]) if swap else (row[4], row[5])
-        raise ParameterNotTabulated(f"stretch-bend {sbt}:{ti}-{tj}-{tk}")
+        # no typed row: the default rule by periodic-table rows (MMFF94.java:1047-1060); the table is stored with
+        # IR <= KR, the two constants change places when the atoms had to be swapped to look it up
+        ri, rj, rk = (self.periodic_row(t) for t in (ti, tj, tk))
+        hit = self.stbn_default.get((min(ri, rk), rj, max(ri, rk)))
+        if hit is None:
+            raise ParameterNotTabulated(f"stretch-bend {sbt}:{ti}-{tj}-{tk}")
+        return (hit[1], hit[0]) if ri > rk else hit
+
+    def periodic_row(self, t: int) -> int:
+        """Row of the periodic table as the stretch-bend default rule counts it (MMFF94.java:1064-1080)."""
+        z = self.geom_row(t).atomic_number
+        for row, last in enumerate((2, 10, 18, 36, 54, 86)):
+            if z <= last:
+                return row
+        return 6
 
     def find_oop(self, ti: int, tj: int, tk: int, tl: int) -> Optional[np.float32]:
         """Returns koop, or ``None`` where the reference stores a null row."""

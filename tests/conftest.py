@@ -21,6 +21,13 @@ def golden_names(pinned_only=True):
     return list(m["pinned"]) + ([] if pinned_only else list(m["unpinned"]))
 
 
+def golden_tolerance(name):
+    """kcal/mol within which the fixture reproduced the published OPTIMOL total when it was generated: 1e-5, or
+    1e-4 for the molecules listed under "tolerance" (tests/golden/make_golden.py explains the two levels)."""
+    with open(os.path.join(GOLDEN_DIR, "MANIFEST.json")) as fh:
+        return float(json.load(fh).get("tolerance", {}).get(name, 1e-5))
+
+
 def load_golden(name):
     from jmolecularenergy_b200.system import MolecularSystem
     return MolecularSystem.load(os.path.join(GOLDEN_DIR, f"{name}.json"))

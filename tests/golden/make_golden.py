@@ -14,10 +14,18 @@ For each hand-typed molecule of the reference's MMFF94 validation suite
 3. looks every parameter up in the reference's ``.par`` tables (table hits only, see
    ``jmolecularenergy_b200/builder.py``),
 4. evaluates the pure-Python restatement (``oracle/py_oracle.py``) and keeps the
-   molecule only if it reproduces the published total to 1e-5 kcal/mol.
+   molecule only if it reproduces the published total AND its bond-charge-increment charges
+   round to the USER_CHARGES column of the mol2 record.
 
-A molecule that fails step 4 is reported and skipped - that means the hand typing (or a
+A molecule that fails step 4 is reported and skipped - that means the typing (or a
 needed empirical rule) is wrong, and it must not become a fixture.
+
+Besides the hand-typed molecules, every ACYCLIC, neutral record of the suite is typed by a small rule
+set (``auto_types``: neighbour counts and bond orders only - no ring or aromaticity perception, so ring
+systems are left alone) and goes through the same two checks.  The checks are what makes this safe: over
+the suite a correct typing lands within 6e-5 kcal/mol of the published value (the published numbers carry
+5 decimals and OPTIMOL's own rounding), a wrong one is off by more than 1 kcal/mol, with nothing in
+between.  The tolerance a fixture met (1e-5 or 1e-4) is recorded in MANIFEST.json and is what the tests use.
 """
 from __future__ import annotations
 
@@ -79,6 +87,132 @@ HAND_TYPED = {
     "SI02A":  ([19, 1, 5, 5, 5, 5, 5, 5], {}),                 # methylsilane
     "SI03A":  ([19, 1, 6, 5, 5, 5, 5, 5, 21], {}),             # methyl hydroxyl silane
 }
+
+
+def auto_types(atoms, bonds):
+    """MMFF numeric types for an acyclic, neutral molecule from connectivity and bond orders alone, or None when
+    the molecule is outside what these rules cover.  Types (MMFFSYMB): C 1 alkyl / 2 vinylic / 3 C=O, C=N, C=S /
+    4 sp; H 5 on C, Si / 21 alcohol / 24 acid, on P-O / 29 enol / 33 on S-O / 23 amine / 28 amide, enamine,
+    sulfonamide / 27 imine / 71 on S, P / 31 water; O 6 divalent / 7 carbonyl, nitroso, sulfoxide / 32 terminal O
+    on N (nitro), S (sulfone...), P / 70 water; N 8 amine / 9 imine, azo / 10 amide, hydrazone N / 40 enamine /
+    42 nitrile / 43 sulfonamide / 45 nitro / 46 nitroso; S 15 / 16 thiocarbonyl / 17 sulfoxide / 18 sulfone;
+    P 26 / 25; Si 19; halogens 11-14."""
+    n = len(atoms)
+    el = [a[0] for a in atoms]
+    nb = [[] for _ in range(n)]
+    for a, b, o in bonds:
+        o = "1" if o == "am" else o
+        if o not in ("1", "2", "3"):
+            return None
+        nb[a].append((b, int(o)))
+        nb[b].append((a, int(o)))
+    if len(bonds) != n - 1:                   # a tree: acyclic and connected
+        return None
+
+    def double_to(i, els):
+        return any(o == 2 and el[j] in els for j, o in nb[i])
+
+    def top(i):
+        return max((o for _, o in nb[i]), default=0)
+
+    t = [0] * n
+    for i in range(n):
+        e, deg, mo = el[i], len(nb[i]), top(i)
+        if e == "C":
+            if deg == 4:
+                t[i] = 1
+            elif deg == 3 and mo == 2:
+                t[i] = 3 if double_to(i, ("O", "N", "S")) else 2
+            elif deg == 2 and (mo == 3 or sum(o == 2 for _, o in nb[i]) == 2):
+                t[i] = 4
+            else:
+                return None
+        elif e == "O":
+            if deg == 2:
+                t[i] = 70 if all(el[j] == "H" for j, _ in nb[i]) else 6
+            elif deg == 1:
+                j, o = nb[i][0]
+                if el[j] == "C" and o == 2:
+                    t[i] = 7
+                elif el[j] == "N":
+                    t[i] = 7 if len(nb[j]) == 2 else 32
+                elif el[j] == "S":
+                    terminal = sum(1 for k, _ in nb[j] if el[k] == "O" and len(nb[k]) == 1)
+                    t[i] = 7 if (len(nb[j]) == 3 and terminal == 1) else 32
+                elif el[j] == "P":
+                    t[i] = 32
+                else:
+                    return None
+            else:
+                return None
+        elif e == "S":
+            t[i] = {(2, 1): 15, (1, 2): 16}.get((deg, mo), {3: 17, 4: 18}.get(deg, 0))
+            if not t[i]:
+                return None
+        elif e == "P":
+            t[i] = {3: 26, 4: 25}.get(deg, 0)
+            if not t[i]:
+                return None
+        elif e == "SI":
+            t[i] = 19
+        elif e in ("F", "CL", "BR", "I"):
+            if deg != 1:
+                return None
+            t[i] = {"F": 11, "CL": 12, "BR": 13, "I": 14}[e]
+        elif e not in ("N", "H"):
+            return None
+    for i in range(n):                           # nitrogen: needs its neighbours' environment
+        if el[i] != "N":
+            continue
+        deg, mo = len(nb[i]), top(i)
+        if deg == 1 and mo == 3:
+            t[i] = 42
+        elif deg == 2 and mo == 2:
+            t[i] = 46 if double_to(i, ("O",)) else 9
+        elif deg == 3 and mo == 2:
+            t[i] = 45
+        elif deg == 3 and mo == 1:
+            kind = 8
+            if any(el[j] == "C" and double_to(j, ("O", "S")) for j, _ in nb[i]):
+                kind = 10
+            elif any(el[j] == "N" and top(j) == 2 for j, _ in nb[i]):
+                kind = 10
+            elif any(el[j] == "S" and len(nb[j]) == 4 for j, _ in nb[i]):
+                kind = 43
+            elif any(el[j] == "C" and top(j) >= 2 for j, _ in nb[i]):
+                kind = 40
+            t[i] = kind
+        else:
+            return None
+    for i in range(n):                           # hydrogen: by the atom it sits on
+        if el[i] != "H":
+            continue
+        if len(nb[i]) != 1:
+            return None
+        j = nb[i][0][0]
+        e = el[j]
+        if e in ("C", "SI"):
+            t[i] = 5
+        elif e in ("S", "P"):
+            t[i] = 71
+        elif e == "N":
+            t[i] = {8: 23, 10: 28, 40: 28, 43: 28, 9: 27}.get(t[j], 0)
+        elif e == "O":
+            if t[j] == 70:
+                t[i] = 31
+            else:
+                x = [k for k, _ in nb[j] if k != i]
+                if len(x) == 1:
+                    x = x[0]
+                    if el[x] == "C":
+                        t[i] = 24 if double_to(x, ("O",)) else (29 if t[x] in (2, 3) else 21)
+                    elif el[x] == "S":
+                        t[i] = 33
+                    elif el[x] == "P":
+                        t[i] = 24
+        if not t[i]:
+            return None
+    return t
 
 
 def read_mol2(path):
@@ -238,8 +372,14 @@ def main():
     tables = MMFFTables(PAR_DIR)
     mols = read_mol2(MOL2)
     energies = read_energies(ENERGIES)
-    kept, report = [], []
-    for name, (typing, ion_charges) in HAND_TYPED.items():
+    kept, report, tolerance = [], [], {}
+    candidates = [(name, HAND_TYPED[name], "hand-assigned") for name in HAND_TYPED]
+    for name in mols:
+        if name not in HAND_TYPED and name in energies:
+            guess = auto_types(mols[name]["atoms"], mols[name]["bonds"])
+            if guess is not None:
+                candidates.append((name, (guess, {}), "rule-assigned (auto_types)"))
+    for name, (typing, ion_charges), how in candidates:
         m = mols[name]
         if callable(typing):
             types = [typing(a[0]) for a in m["atoms"]]
@@ -251,7 +391,7 @@ def main():
         orders = [{"1": 1, "2": 2, "3": 3, "am": 1, "ar": 1}[o] for _, _, o in m["bonds"]]
         expected, eline = energies[name]
         src = (f"MMFF94_dative.mol2:{m['line']} / MMFF94.energies:{eline} (OPTIMOL); "
-               f"hand-assigned types {types}")
+               f"{how} types {types}")
         try:
             s = parameterize(tables, xyz, types, bonds, formal, orders, name=name,
                              expected_energy=expected, source=src)
@@ -259,7 +399,8 @@ def main():
             report.append(f"SKIP {name}: needs an empirical rule ({exc})")
             continue
         got = py_oracle.energy_components(s)
-        ok = abs(got["total"] - expected) <= 1e-5
+        diff = abs(got["total"] - expected)
+        ok = diff <= 1e-4
         # mol2 USER_CHARGES are printed to 4 decimals: the bci charges must round to them
         qok = np.allclose(s.charge, [a[4] for a in m["atoms"]], atol=5.1e-5)
         report.append(f"{'KEEP' if ok and qok else 'FAIL'} {name}: E={got['total']:.6f} "
@@ -267,6 +408,8 @@ def main():
         if ok and qok:
             s.save(os.path.join(HERE, f"{name}.json"))
             kept.append(name)
+            if diff > 1e-5:
+                tolerance[name] = 1e-4
     # ethanol: config-1 input, no published value
     xyz, types, bonds = ethanol_geometry()
     s = parameterize(tables, xyz, types, bonds, name="ETHANOL",
@@ -279,7 +422,7 @@ def main():
                   f"terms: {len(s.bond_i)} bonds {len(s.angle_i)} angles {len(s.oop_i)} oop "
                   f"{len(s.tor_i)} torsions")
     with open(os.path.join(HERE, "MANIFEST.json"), "w") as fh:
-        json.dump({"pinned": kept, "unpinned": ["ETHANOL"]}, fh, indent=1)
+        json.dump({"pinned": kept, "unpinned": ["ETHANOL"], "tolerance": tolerance}, fh, indent=1)
         fh.write("\n")
     report += write_templates(tables)
     print("\n".join(report))

@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from conftest import golden_names, load_golden
+from conftest import golden_names, golden_tolerance, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -42,11 +42,12 @@ def assert_parity(got, ref, label=""):
 
 @pytest.mark.parametrize("name", PINNED)
 def test_golden_energy_matches_published_value(name):
-    """The reference's own criterion (MMFF94Test.java:79-81) through the GPU path, at 1e-5 not 1e-2."""
+    """The reference's own criterion (MMFF94Test.java:79-81) through the GPU path, at 1e-5 (1e-4 for the fixtures
+    MANIFEST.json lists) not 1e-2."""
     s = load_golden(name)
     ff = gpu_ff()
     ff.assignParameters(s)
-    assert abs(ff.calculateEnergy(s) - s.expected_energy) <= 1e-5
+    assert abs(ff.calculateEnergy(s) - s.expected_energy) <= golden_tolerance(name)
 
 
 @pytest.mark.parametrize("name", ALL)
