@@ -440,3 +440,34 @@ def test_cell_path_grows_its_lists_for_dense_systems(oracle):
     assert_parity(got, ref, "dense")
     pi, pj, f14 = ff.pairList(s)
     assert len(pi) == ref["pairs"]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_random_systems_both_cutoff_paths(oracle, seed):
+    """Randomised sweep over sizes, densities and cutoffs (group / chunk / trip boundaries of the cell path fall
+    differently every time): cell path == all-pairs path == oracle, pair counts included."""
+    from jmolecularenergy_b200 import systems
+    rng = np.random.default_rng(1000 + seed)
+    kind = seed % 3
+    if kind == 0:
+        s = systems.ion_box(int(rng.integers(5, 15)), seed=seed, spacing=float(rng.uniform(1.8, 3.2)))
+    elif kind == 1:
+        s = systems.water_box(int(rng.integers(40, 900)), seed=seed)
+    else:
+        s = systems.solvated_chains(int(rng.integers(1500, 5000)), chain_fraction=float(rng.uniform(0.1, 0.5)), seed=seed)
+    s.xyz[:] = s.xyz + rng.normal(0, 0.05, size=s.xyz.shape)
+    cutoff = float(rng.uniform(3.5, 11.0))
+    ref = oracle.evaluate(s, cutoff=cutoff, gradient=True) if s.n_atoms <= 1200 else \
+        oracle.fast_evaluate(s, cutoff=cutoff, gradient=True)
+    for path in ("cells", "allpairs"):
+        ff = gpu_ff(path=path, cutoff=cutoff)
+        ff.assignParameters(s)
+        got = ff.calculateComponents(s, gradient=True)
+        assert got["pairs"] == ref["pairs"], (path, seed, got["pairs"], ref["pairs"])
+        for k in ("vdw", "ele"):
+            scale = max(abs(ref[k]), 1e-3)
+            assert abs(got[k] - ref[k]) <= E_RTOL * scale, (path, seed, k, got[k], ref[k])
+        if s.n_atoms <= 1200:
+            assert_parity(got, ref, f"{path} seed {seed}")
+        e_only = ff.calculateEnergy(s)
+        assert e_only == pytest.approx(got["total"], rel=1e-13)
