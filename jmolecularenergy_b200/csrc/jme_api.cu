@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -13,6 +14,7 @@
 
 #include "../../include/jme_b200.h"
 #include "jme_cells.cuh"
+#include "jme_clusters.cuh"
 #include "jme_host.hpp"
 #include "jme_kernels.cuh"
 
@@ -339,8 +341,15 @@ int ensure_plan(jme_handle* h) {
     if (p == JME_PATH_ALLPAIRS) {
         if ((rc = build_allpairs_plan(h))) return rc;
     } else {
-        if ((rc = build_cell_plan(h->cells, h->hs, h->ds, h->cutoff, h->rank, h->world, h->err))) return rc;
+        // JME_CLUSTER (development knob): atoms per cluster of the cutoff path, 2 or 4; 0 = the round-1 per-atom lists
+        int cluster = 4;
+        if (const char* e = std::getenv("JME_CLUSTER")) cluster = std::atoi(e);
+        if (cluster != 0 && cluster != 2 && cluster != 4) cluster = 4;
+        if (h->cells.built && h->cells.cluster != cluster) cluster = h->cells.cluster;
+        rc = build_cell_plan(h->cells, h->hs, h->ds, h->cutoff, h->rank, h->world, cluster, h->err);
         for (void* q : h->cells.take_new_allocs()) h->mem.ptrs.push_back(q);
+        if (rc) return rc;
+        if (cluster != 0 && (rc = cl_configure(h->cells, h->ds, h->err))) return rc;
     }
     if ((rc = build_bonded_plan(h))) return rc;
     h->active_path = p;
@@ -423,6 +432,14 @@ int enqueue_launches(jme_handle* h, bool grad, double* d_out_user, bool fork) {
         if (rc) return rc;
         A.gpart = h->d_gpart; A.n_slots = h->n_slots; A.direct = nullptr;
         A.epart = h->d_epart; A.cpart = h->d_cpart; A.n_epart = h->n_epart;
+    } else if (h->cells.cluster != 0) {
+        if ((rc = run_cell_sort(h->cells, h->ds, h->stream, h->launches, h->err))) return rc;
+        if ((rc = cl_run_lists(h->cells, h->ds, h->stream, h->launches, h->err))) return rc;
+        if (pe) cudaEventRecord(pe[1], h->stream);
+        if ((rc = cl_run_pairs(h->cells, h->ds, grad, h->stream, h->launches, h->err))) return rc;
+        A.gpart = nullptr; A.n_slots = 0; A.direct = nullptr;
+        A.overflow = h->cells.arr.flags;
+        A.epart = h->cells.d_epart; A.cpart = h->cells.d_cpart; A.n_epart = 0;      // shard range taken on the device
     } else {
         if ((rc = run_cell_sort(h->cells, h->ds, h->stream, h->launches, h->err))) return rc;
         if ((rc = run_cell_lists(h->cells, h->ds, h->stream, h->launches, h->err))) return rc;
@@ -443,6 +460,8 @@ int enqueue_launches(jme_handle* h, bool grad, double* d_out_user, bool fork) {
     A.want_grad = grad ? 1 : 0;
     A.out = d_out_user ? d_out_user : h->d_out;
     A.out_host = d_out_user ? nullptr : h->h_out_dev;
+    if (h->active_path == JME_PATH_CELLS && h->cells.cluster != 0)
+        return cl_run_reduce(h->cells, h->ds, A, h->stream, h->launches, h->err);
     const int apb = A.n_slots == 0 ? kReduceWarps * 32 : 32;      // atoms per block, see reduce_kernel
     const int grid = grad ? (h->ds.n + apb - 1) / apb + 1 : 1;
     reduce_kernel<<<grid, kReduceWarps * 32, 0, h->stream>>>(A);
@@ -481,6 +500,7 @@ int enqueue_eval(jme_handle* h, bool grad, double* d_out_user) {
             if (graph) cudaGraphDestroy(graph);
             cudaGetLastError();
             h->use_graphs = false;                 // fall back to plain launches for this handle
+            h->cells.coords_changed();             // the sort was only captured, never executed
             return rc ? rc : enqueue_launches(h, grad, d_out_user, false);
         }
         ce = cudaGraphInstantiate(&g.exec, graph, 0);
@@ -489,6 +509,7 @@ int enqueue_eval(jme_handle* h, bool grad, double* d_out_user) {
             g.exec = nullptr;
             cudaGetLastError();
             h->use_graphs = false;
+            h->cells.coords_changed();
             return enqueue_launches(h, grad, d_out_user, false);
         }
         g.epoch = h->graph_epoch; g.out = out; g.stream = h->stream;
@@ -508,7 +529,12 @@ int finish_host(jme_handle* h, bool grad, double* total, double* comps, double* 
     if (comps) for (int c = 0; c < JME_N_COMPONENTS; ++c) comps[c] = h->h_out[1 + c];
     h->last_pairs = (uint64_t)h->h_out[8];
     h->last_cand = (uint64_t)h->h_out[9];
-    if (h->active_path == JME_PATH_CELLS && h->h_out[kOutHeader] != 0.0) return kListOverflow;
+    if (h->active_path == JME_PATH_CELLS && h->h_out[kOutHeader] != 0.0) {
+        const int f = (int)h->h_out[kOutHeader];
+        if (f & 2) return fail(h, JME_ERR_UNSUPPORTED, "cell path: a cell row window holds more atoms than the list entry format addresses (density too high for this cutoff)");
+        if (f & 1) return kListOverflow;
+        // f & 4: a non-finite coordinate - the total is NaN, which is the answer
+    }
     return JME_OK;
 }
 
@@ -849,7 +875,10 @@ int jme_pair_list(jme_handle_t* h, int32_t* pair_i, int32_t* pair_j, uint8_t* is
     } else {
         // a truncated survivor list would silently drop pairs: grow the lists and redo, like eval_host
         for (;;) {
-            rc = run_cell_pairlist(h->cells, h->ds, d_i, d_j, d_f, capacity, d_cur, h->stream, h->launches, h->err);
+            h->cells.coords_changed();
+            rc = h->cells.cluster != 0
+                     ? cl_run_pairlist(h->cells, h->ds, d_i, d_j, d_f, capacity, d_cur, h->stream, h->launches, h->err)
+                     : run_cell_pairlist(h->cells, h->ds, d_i, d_j, d_f, capacity, d_cur, h->stream, h->launches, h->err);
             if (rc || cudaStreamSynchronize(h->stream) != cudaSuccess || !cell_overflowed(h->cells)) break;
             if ((rc = grow_cell_lists(h))) break;
             ++h->graph_epoch;

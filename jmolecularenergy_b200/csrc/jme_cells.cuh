@@ -51,6 +51,11 @@ struct GridParams {
     float r2f_max;           // conservative FP32 candidate threshold on r^2
     double cutoff_pad;       // cutoff + margin used for row culling
     float edge_f, inv_edge_f, cut2_pad_f;   // FP32 copies for the per-row culling (margins included)
+    // cluster path (jme_clusters.cuh): half shell of neighbour rows and the segment decomposition of the cell rows
+    int n_half;              // rows in the half shell: reach * (2 reach + 1) + reach + 1  (13 for reach 2)
+    int seg_len;             // cells per segment along x (>= 2 reach + 1)
+    int nsx;                 // segments per cell row
+    int n_seg;               // ny * nz * nsx
 };
 
 struct alignas(32) PosQ { double x, y, z, q; };
@@ -68,17 +73,21 @@ __device__ __forceinline__ PosQ load_posq(const PosQ* p) {
 struct CellArrays {
     GridParams* grid;
     int n, n_pad, max_cells;
+    int pad;                 // every cell is padded to a multiple of `pad` sorted positions (1: no padding)
+    int n_spad;              // capacity of the arrays indexed by sorted position: n + (pad - 1) * min(n, max_cells)
+    int seg_target;          // wanted number of segments (cluster path), 0 otherwise
+    int* flags;              // [4] device flags: [0] list overflow, [1] non-finite coordinate, [2] window fallback used
     int* cell_of;            // [n] cell index per original atom
     int* count;              // [max_cells + 1]
     int* start;              // [max_cells + 1]
     int* cursor;             // [max_cells]
     int* block_sums;         // scan scratch
-    int* order_tmp;          // [n]
-    int* orig;               // [n] sorted position -> original atom
-    int* scell;              // [n] cell of sorted position
-    PosQ* spq;               // [n] sorted x, y, z, q: one 32-byte record = one sector, one 256-bit load per gather
-    float4* fxyz;            // [n] sorted positions relative to the grid origin, FP32; w = type index (int bits)
-    int* stype;              // [n] type index by sorted position
+    int* order_tmp;          // [n_spad]
+    int* orig;               // [n_spad] sorted position -> original atom (-1: padding)
+    int* scell;              // [n_spad] cell of sorted position
+    PosQ* spq;               // [n_spad] sorted x, y, z, q: one 32-byte record = one sector, one 256-bit load per gather
+    float4* fxyz;            // [n_spad] sorted positions relative to the grid origin, FP32; w = type index (int bits)
+    int* stype;              // [n_spad] type index by sorted position
     int* sorted_of;          // [n] original atom -> sorted position
     const long long* excl_ptr;    // CSR over original atom index
     const unsigned int* excl_ent; // partners by original index (bit 31 = 1-4 pair)
@@ -86,17 +95,22 @@ struct CellArrays {
     long long n_excl_ent;
     double* bbox_part;       // [blocks][6]
     int bbox_blocks;
-    int* work_ctr;           // [2] dynamic work distribution: next (cell, part) item / next atom group
+    int* work_ctr;           // [2] dynamic work distribution: next (cell, part) item / next atom group (or segment);
+                             // work_ctr and flags are one 32-byte control block
 };
 
 // ---- 1. bounding box ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bbox_kernel(DeviceSystem S, double* __restrict__ part) {
+__global__ void __launch_bounds__(256) bbox_kernel(DeviceSystem S, double* __restrict__ part, int* __restrict__ flags) {
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    bool bad = false;
     for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < S.n; a += gridDim.x * blockDim.x) {
         const double v[3] = {S.x[a], S.y[a], S.z[a]};
+        // a non-finite coordinate has no cell: it stays out of the box and poisons the result (NaN total)
+        if (!(fabs(v[0]) < 1e300 && fabs(v[1]) < 1e300 && fabs(v[2]) < 1e300)) { bad = true; continue; }
 #pragma unroll
         for (int c = 0; c < 3; ++c) { lo[c] = fmin(lo[c], v[c]); hi[c] = fmax(hi[c], v[c]); }
     }
+    if (bad) flags[1] = 1;
     __shared__ double s[8][6];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
@@ -115,7 +129,8 @@ __global__ void __launch_bounds__(256) bbox_kernel(DeviceSystem S, double* __res
     }
 }
 
-__global__ void grid_setup_kernel(const double* __restrict__ part, int n_part, double cutoff, int max_cells, GridParams* g) {
+__global__ void grid_setup_kernel(const double* __restrict__ part, int n_part, double cutoff, int max_cells, int seg_target,
+                                  GridParams* g) {
     // one warp: lanes stride over the per-block bounding boxes, shuffle min/max, lane 0 derives the grid
     const int lane = threadIdx.x;
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
@@ -128,23 +143,44 @@ __global__ void grid_setup_kernel(const double* __restrict__ part, int n_part, d
         }
     if (lane != 0) return;
     double ext[3], extent = 0;
-    for (int c = 0; c < 3; ++c) { ext[c] = fmax(hi[c] - lo[c], 0.0); extent = fmax(extent, ext[c]); }
-    // cell edge: half the cutoff (5x5x5 stencil, about 27 % of it inside the sphere before row culling),
-    // grown if the box would need more cells than were allocated
-    double edge = 0.5 * cutoff;
-    for (;;) {
+    for (int c = 0; c < 3; ++c) {
+        if (!(lo[c] <= hi[c])) { lo[c] = 0; hi[c] = 0; }          // no finite atom at all
+        ext[c] = fmax(hi[c] - lo[c], 0.0);
+        extent = fmax(extent, ext[c]);
+    }
+    // cell edge: half the cutoff plus a hair (5x5x5 stencil; the hair keeps two atoms at exactly r == cutoff within two
+    // cells of each other whatever floor() does at the cell boundaries), grown if the box would need more cells than
+    // were allocated.  The growth is bounded: 400 steps of x1.25 cover any finite extent.
+    double edge = 0.5 * cutoff * (1.0 + 1e-9);
+    g->nx = g->ny = g->nz = 1;
+    for (int it = 0; it < 400; ++it) {
         const double nx = floor(ext[0] / edge) + 1, ny = floor(ext[1] / edge) + 1, nz = floor(ext[2] / edge) + 1;
         if (nx * ny * nz <= (double)max_cells) {
             g->nx = (int)nx; g->ny = (int)ny; g->nz = (int)nz;
             break;
         }
         edge *= 1.25;
+        if (it == 399) edge = fmax(extent, cutoff) * 2.0;          // unreachable for finite input: one cell
     }
     g->ox = lo[0]; g->oy = lo[1]; g->oz = lo[2];
     g->edge = edge;
     g->inv_edge = 1.0 / edge;
     g->ncell = g->nx * g->ny * g->nz;
     g->reach = (int)ceil(cutoff / edge);
+    if (g->reach < 1) g->reach = 1;
+    if (g->reach > 2) g->reach = 2;                               // edge >= cutoff / 2 by construction
+    {   // segments of the cell rows for the cluster path: about seg_target of them, at least 2 reach + 1 cells long
+        const int rows = g->ny * g->nz;
+        const int lmin = 2 * g->reach + 1;
+        int nsx = seg_target > 0 ? (seg_target + rows - 1) / rows : 1;
+        int len = g->nx / (nsx > 0 ? nsx : 1);
+        if (len < lmin) len = lmin;
+        if (len > 12) len = 12;                                   // kClMaxSegLen: per-warp window tables are this long
+        g->seg_len = len;
+        g->nsx = (g->nx + len - 1) / len;
+        g->n_seg = rows * g->nsx;
+        g->n_half = g->reach * (2 * g->reach + 1) + g->reach + 1;
+    }
     // FP32 candidate test on positions relative to the origin: coordinate error <= extent * 2^-24 each,
     // so |r_f - r| <= 4 * extent * 2^-23 with room to spare; r2 margin = 2 r dr + float product rounding
     const double dr = 8.0 * (extent + cutoff) * 1.1920929e-7 + 1e-6;
@@ -186,13 +222,14 @@ __global__ void cell_assign_kernel(DeviceSystem S, const GridParams* __restrict_
 
 // exclusive scan of count[0..ncell] -> start[0..ncell] in three small launches
 __global__ void __launch_bounds__(kScanBlock) scan_local_kernel(const GridParams* __restrict__ g, const int* __restrict__ count,
-                                                                int* __restrict__ start, int* __restrict__ block_sums) {
+                                                                int* __restrict__ start, int* __restrict__ block_sums, int pad) {
     const int total = g->ncell + 1;
     const int base = blockIdx.x * kScanBlock;
     if (base >= total) return;
     __shared__ int s[kScanBlock];
     const int i = base + threadIdx.x;
-    const int v = i < total ? count[i] : 0;
+    // cells are padded to a multiple of `pad` sorted positions (cluster path): start[] runs over the padded sizes
+    const int v = i < total ? (count[i] + pad - 1) / pad * pad : 0;
     s[threadIdx.x] = v;
     __syncthreads();
     for (int o = 1; o < kScanBlock; o <<= 1) {
@@ -246,15 +283,16 @@ __global__ void cell_scatter_kernel(int n, const int* __restrict__ cell_of, cons
     order_tmp[start[c] + atomicAdd(&cursor[c], 1)] = a;
 }
 
-// position p of the atomics-ordered list -> its rank among the atoms of its cell by original index
+// atom a -> its rank among the atoms of its cell by original index (the atomics-ordered scatter only groups the
+// atoms by cell), then the gather into the sorted arrays.  With padded cells (cluster path) the last atom of a cell
+// also writes the cell's padding records: far away, never selected by the FP32 test (NaN) nor by the exact one
 __global__ void cell_rank_gather_kernel(DeviceSystem S, CellArrays C) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= S.n) return;
-    const int a = C.order_tmp[p];
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= S.n) return;
     const int c = C.cell_of[a];
-    const int b = C.start[c], e = C.start[c + 1];
+    const int b = C.start[c], m = C.count[c];
     int rank = 0;
-    for (int q = b; q < e; ++q) rank += C.order_tmp[q] < a;
+    for (int q = b; q < b + m; ++q) rank += C.order_tmp[q] < a;
     const int d = b + rank;
     const GridParams* g = C.grid;
     C.orig[d] = a;
@@ -266,6 +304,17 @@ __global__ void cell_rank_gather_kernel(DeviceSystem S, CellArrays C) {
     C.stype[d] = t;
     C.sorted_of[a] = d;
     C.fxyz[d] = make_float4((float)(x - g->ox), (float)(y - g->oy), (float)(z - g->oz), __int_as_float(t));
+    if (C.pad > 1 && rank == m - 1) {
+        const int e = C.start[c + 1];
+        for (int q = b + m; q < e; ++q) {
+            C.orig[q] = -1;
+            C.scell[q] = c;
+            PosQ f; f.x = f.y = f.z = 1e100; f.q = 0.0;
+            C.spq[q] = f;
+            C.stype[q] = 0;
+            C.fxyz[q] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, __int_as_float(0));
+        }
+    }
 }
 
 // exclusion / 1-4 rows with the partners renamed to sorted positions: the evaluation kernel then compares list
@@ -669,7 +718,8 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
                     unsigned int e = b2 + 32 * k + lane < hits2 ? src[32 * k] : (unsigned int)base;
                     // the address carries a (never taken) dependence on r2, so that this load is issued after the
                     // wait for this trip's operands and not before it
-                    e = max(e, (unsigned int)(__double2hiint(r2[k]) >> 31));
+                    // (a NaN r2 may carry the sign bit: the mask keeps the index inside the arrays)
+                    e = max(e, ((unsigned int)__double2hiint(r2[k]) >> 31) & (e >> 31));
                     gather(nx, k, e);
                 }
             }
@@ -772,15 +822,25 @@ struct CellPlan {
     unsigned long long* d_cpart = nullptr;
     int n_epart = 0, epart_cap = 0;
     int grid_pairs = 0;
-    int i_begin = 0, i_end = 0, world = 1;
+    int i_begin = 0, i_end = 0, world = 1, rank = 0;
     unsigned int* d_list = nullptr;
     int* d_count = nullptr;
-    int* d_overflow = nullptr;
+    int* d_overflow = nullptr;     // = arr.flags
     int list_cap = 0;
     int grid_list = 0;
     double cutoff = 0;
     bool built = false;
     bool sorted_valid = false;
+    // cluster path (jme_clusters.cuh); cluster == 0: the round-1 per-atom survivor lists
+    int cluster = 0;
+    int n_spad = 0;
+    int sms = 148;
+    int cl_warps = 0, cl_table_in_smem = 1;
+    size_t cl_smem_grad = 0, cl_smem_energy = 0;
+    double* d_gi = nullptr;
+    double* d_gj = nullptr;
+    double* d_gj_ovf = nullptr;
+    int* d_excl_src = nullptr;
     std::vector<void*> new_allocs;
 
     std::vector<void*> take_new_allocs() { std::vector<void*> v; v.swap(new_allocs); return v; }
@@ -797,27 +857,48 @@ inline bool cell_alloc(CellPlan& p, T** out, size_t count, std::string& err) {
     return true;
 }
 
+// `cluster` = 0: round-1 per-atom survivor lists; 2 or 4: cluster path (jme_clusters.cuh), cells padded to that size
 inline int build_cell_plan(CellPlan& p, const HostSystem& hs, const DeviceSystem& ds, double cutoff, int rank, int world,
-                           std::string& err) {
+                           int cluster, std::string& err) {
     const int n = ds.n;
-    if ((long long)n > (1ll << kEntryBits) || ds.n_types > 256) {
-        err = "cell path: at most 2^24 atoms and 256 atom types (survivor-list entries are 24 + 8 bits)";
+    if (cluster == 0 && ((long long)n > (1ll << kEntryBits) || ds.n_types > 256)) {
+        err = "cell path (per-atom lists): at most 2^24 atoms and 256 atom types (survivor-list entries are 24 + 8 bits)";
         return JME_ERR_UNSUPPORTED;
+    }
+    if (cluster != 0 && ds.n_types > 128) {
+        err = "cell path: at most 128 atom types (list entries carry 7 type bits)";
+        return JME_ERR_UNSUPPORTED;
+    }
+    if ((long long)n * std::max(1, cluster) > 0x7fffff00ll) {
+        err = "cell path: too many atoms for 32-bit sorted positions";
+        return JME_ERR_UNSUPPORTED;
+    }
+    if (p.built && p.cluster != cluster) {
+        err = "internal: the cell plan cannot change its cluster size";
+        return JME_ERR_INVALID;
     }
     if (!p.built) {
         CellArrays& a = p.arr;
+        p.cluster = cluster;
         a.n = n; a.n_pad = ds.n_pad;
         a.max_cells = std::max(4096, 4 * n);
+        a.pad = std::max(1, cluster);
+        // padded cells: at most (pad - 1) padding records per non-empty cell
+        a.n_spad = p.n_spad = n + (a.pad - 1) * std::min(n, a.max_cells);
         a.bbox_blocks = std::max(1, std::min(592, (n + 255) / 256));
         const int scan_blocks = (a.max_cells + 1 + kScanBlock - 1) / kScanBlock;
+        const size_t ns = (size_t)p.n_spad + 1;          // + 1: see the gather of cl_pair_kernel
         bool ok = cell_alloc(p, &a.grid, 1, err) && cell_alloc(p, &a.cell_of, n, err) && cell_alloc(p, &a.count, a.max_cells + 1, err) &&
                   cell_alloc(p, &a.start, a.max_cells + 1, err) && cell_alloc(p, &a.cursor, a.max_cells, err) &&
-                  cell_alloc(p, &a.block_sums, scan_blocks, err) && cell_alloc(p, &a.order_tmp, n, err) &&
-                  cell_alloc(p, &a.orig, n, err) && cell_alloc(p, &a.scell, n, err) && cell_alloc(p, &a.spq, n, err) &&
-                  cell_alloc(p, &a.fxyz, n, err) && cell_alloc(p, &a.stype, n, err) && cell_alloc(p, &a.sorted_of, n, err) && cell_alloc(p, &a.bbox_part, 6 * (size_t)a.bbox_blocks, err) &&
-                  cell_alloc(p, &a.work_ctr, 2, err) &&
-                  cell_alloc(p, &p.d_grad, 3 * (size_t)ds.n_pad, err);
+                  cell_alloc(p, &a.block_sums, scan_blocks, err) && cell_alloc(p, &a.order_tmp, ns, err) &&
+                  cell_alloc(p, &a.orig, ns, err) && cell_alloc(p, &a.scell, ns, err) && cell_alloc(p, &a.spq, ns, err) &&
+                  cell_alloc(p, &a.fxyz, ns, err) && cell_alloc(p, &a.stype, ns, err) && cell_alloc(p, &a.sorted_of, n, err) &&
+                  cell_alloc(p, &a.bbox_part, 6 * (size_t)a.bbox_blocks, err) && cell_alloc(p, &a.work_ctr, 8, err);
         if (!ok) return JME_ERR_NOMEM;
+        a.flags = a.work_ctr + 4;
+        p.d_overflow = a.flags;
+        cudaMemset(a.work_ctr, 0, 8 * sizeof(int));
+        cudaMemset(a.spq, 0, ns * sizeof(PosQ));
         long long* d_ptr = nullptr;
         unsigned int* d_ent = nullptr;
         if (!cell_alloc(p, &d_ptr, hs.excl_ptr.size(), err) || !cell_alloc(p, &d_ent, hs.excl_ent.size(), err)) return JME_ERR_NOMEM;
@@ -831,27 +912,47 @@ inline int build_cell_plan(CellPlan& p, const HostSystem& hs, const DeviceSystem
         a.excl_ptr = d_ptr; a.excl_ent = d_ent;
         a.n_excl_ent = (long long)hs.excl_ent.size();
         if (!cell_alloc(p, &a.sexcl_ent, hs.excl_ent.size(), err)) return JME_ERR_NOMEM;
-        // persistent-style launch: enough warps to fill the chip, grid-stride over atoms
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-        p.grid_pairs = std::max(1, std::min((n + kCellWarps - 1) / kCellWarps, sms * JME_CELL_MIN_BLOCKS));
-        p.n_epart = std::max(1, n);           // one energy / count partial per atom group; groups hold >= 1 atom
-        if (!cell_alloc(p, &p.d_epart, 2 * (size_t)p.n_epart, err) || !cell_alloc(p, &p.d_cpart, 2 * (size_t)p.n_epart, err)) return JME_ERR_NOMEM;
-        p.epart_cap = p.n_epart;
-        // survivor lists: fixed capacity per atom (1024 entries; less only if that would exceed 16 GiB)
-        p.list_cap = 1024;
-        while (p.list_cap > 128 && (size_t)n * p.list_cap * sizeof(unsigned int) > ((size_t)16 << 30)) p.list_cap /= 2;
-        if (!cell_alloc(p, &p.d_list, (size_t)std::max(1, n) * p.list_cap, err) || !cell_alloc(p, &p.d_count, n, err) ||
-            !cell_alloc(p, &p.d_overflow, 1, err)) return JME_ERR_NOMEM;
-        cudaMemset(p.d_overflow, 0, sizeof(int));
-        p.grid_list = std::max(1, sms * JME_LIST_MIN_BLOCKS);
+        cudaDeviceGetAttribute(&p.sms, cudaDevAttrMultiProcessorCount, 0);
+        p.grid_list = std::max(1, p.sms * JME_LIST_MIN_BLOCKS);
+        if (cluster == 0) {
+            if (!cell_alloc(p, &p.d_grad, 3 * (size_t)ds.n_pad, err)) return JME_ERR_NOMEM;
+            // persistent-style launch: enough warps to fill the chip, grid-stride over atoms
+            p.grid_pairs = std::max(1, std::min((n + kCellWarps - 1) / kCellWarps, p.sms * JME_CELL_MIN_BLOCKS));
+            p.n_epart = std::max(1, n);           // one energy / count partial per atom group; groups hold >= 1 atom
+            if (!cell_alloc(p, &p.d_epart, 2 * (size_t)p.n_epart, err) || !cell_alloc(p, &p.d_cpart, 2 * (size_t)p.n_epart, err)) return JME_ERR_NOMEM;
+            p.epart_cap = p.n_epart;
+            // survivor lists: fixed capacity per atom (1024 entries; less only if that would exceed 16 GiB)
+            p.list_cap = 1024;
+            while (p.list_cap > 128 && (size_t)n * p.list_cap * sizeof(unsigned int) > ((size_t)16 << 30)) p.list_cap /= 2;
+            if (!cell_alloc(p, &p.d_list, (size_t)std::max(1, n) * p.list_cap, err) || !cell_alloc(p, &p.d_count, n, err)) return JME_ERR_NOMEM;
+            a.seg_target = 0;
+        } else {
+            // one energy / count partial per segment; segments <= cells
+            p.n_epart = p.epart_cap = a.max_cells;
+            if (!cell_alloc(p, &p.d_epart, 2 * (size_t)p.n_epart, err) || !cell_alloc(p, &p.d_cpart, 2 * (size_t)p.n_epart, err)) return JME_ERR_NOMEM;
+            // cluster lists: one per cluster (every cluster holds at least one atom: <= n clusters)
+            p.list_cap = 512;
+            while (p.list_cap > 128 && (size_t)n * p.list_cap * sizeof(unsigned int) > ((size_t)16 << 30)) p.list_cap /= 2;
+            if (!cell_alloc(p, &p.d_list, (size_t)std::max(1, n) * p.list_cap, err) || !cell_alloc(p, &p.d_count, std::max(1, n), err) ||
+                !cell_alloc(p, &p.d_gi, 3 * ns, err) || !cell_alloc(p, &p.d_gj, (size_t)2 * 13 * 3 * ns, err) ||
+                !cell_alloc(p, &p.d_gj_ovf, 3 * ns, err) || !cell_alloc(p, &p.d_excl_src, hs.excl_ent.size(), err))
+                return JME_ERR_NOMEM;
+            std::vector<int> src(hs.excl_ent.size());
+            for (int64_t i = 0; i < hs.n; ++i)
+                for (int64_t e = hs.excl_ptr[i]; e < hs.excl_ptr[i + 1]; ++e) src[(size_t)e] = (int)i;
+            if (!src.empty() && cudaMemcpy(p.d_excl_src, src.data(), src.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+                err = "upload of the exclusion sources failed";
+                return JME_ERR_CUDA;
+            }
+        }
         p.built = true;
     }
-    cudaMemset(p.d_grad, 0, 3 * (size_t)ds.n_pad * sizeof(double));
+    if (p.d_grad) cudaMemset(p.d_grad, 0, 3 * (size_t)ds.n_pad * sizeof(double));
     cudaMemset(p.d_epart, 0, 2 * (size_t)p.epart_cap * sizeof(double));
     cudaMemset(p.d_cpart, 0, 2 * (size_t)p.epart_cap * sizeof(unsigned long long));
     p.cutoff = cutoff;
     p.world = world;
+    p.rank = rank;
     p.i_begin = (int)((long long)n * rank / world);
     p.i_end = (int)((long long)n * (rank + 1) / world);
     p.sorted_valid = false;
@@ -877,11 +978,12 @@ inline int run_cell_sort(CellPlan& p, const DeviceSystem& ds, cudaStream_t st, u
     if (n == 0) { p.sorted_valid = true; return JME_OK; }
     const int nb = (n + 255) / 256;
     const int scan_blocks = (a.max_cells + 1 + kScanBlock - 1) / kScanBlock;
-    bbox_kernel<<<a.bbox_blocks, 256, 0, st>>>(ds, a.bbox_part);
-    grid_setup_kernel<<<1, 32, 0, st>>>(a.bbox_part, a.bbox_blocks, p.cutoff, a.max_cells, a.grid);
+    cudaMemsetAsync(a.work_ctr, 0, 8 * sizeof(int), st);          // work counters and flags
+    bbox_kernel<<<a.bbox_blocks, 256, 0, st>>>(ds, a.bbox_part, a.flags);
+    grid_setup_kernel<<<1, 32, 0, st>>>(a.bbox_part, a.bbox_blocks, p.cutoff, a.max_cells, a.seg_target, a.grid);
     zero_counts_kernel<<<std::min(592, (a.max_cells + 256) / 256), 256, 0, st>>>(a.grid, a.count, a.cursor);
     cell_assign_kernel<<<nb, 256, 0, st>>>(ds, a.grid, a.cell_of, a.count);
-    scan_local_kernel<<<scan_blocks, kScanBlock, 0, st>>>(a.grid, a.count, a.start, a.block_sums);
+    scan_local_kernel<<<scan_blocks, kScanBlock, 0, st>>>(a.grid, a.count, a.start, a.block_sums, a.pad);
     scan_sums_kernel<<<1, 1024, 0, st>>>(a.grid, a.block_sums);
     scan_add_kernel<<<scan_blocks, kScanBlock, 0, st>>>(a.grid, a.start, a.block_sums);
     cell_scatter_kernel<<<nb, 256, 0, st>>>(n, a.cell_of, a.start, a.cursor, a.order_tmp);

@@ -503,12 +503,62 @@ struct ReduceArgs {
     double* out;                    // [0] total [1..7] comps [8] pairs evaluated [9] candidates [10..] gradient AoS
     double* out_host;               // optional: mapped pinned host copy of the header (zero-copy result), kOutHeader + 1
                                     // doubles: [kOutHeader] = overflow flag
-    const int* overflow;            // optional: set when a survivor list of the cell path was truncated
+    const int* overflow;            // optional: the cell paths' device flags [4]: [0] a list was truncated, [1] non-finite
+                                    // coordinate, [2] window fallback used (informational), [3] density beyond the entry format
 };
 constexpr int kOutHeader = 10;
 
 __device__ __forceinline__ double convert_unit(double v, double num, double den) {
     return (num == den) ? v : (v * num) / den;
+}
+
+// energies and pair counts: fixed-order strided sums + shared-memory tree (one block of kReduceWarps * 32 threads)
+__device__ __forceinline__ void reduce_energy_block(const ReduceArgs& A) {
+    constexpr int NT = kReduceWarps * 32;
+    __shared__ double s_e[7][NT];
+    __shared__ unsigned long long s_c[2][NT];
+    double e[7] = {0, 0, 0, 0, 0, 0, 0};
+    unsigned long long c0 = 0, c1 = 0;
+    for (int i = threadIdx.x; i < A.n_bpart; i += NT)
+        for (int c = 0; c < 5; ++c) e[c] += A.bpart[5 * (size_t)i + c];
+    for (int i = threadIdx.x; i < A.n_epart; i += NT) {
+        e[5] += A.epart[2 * (size_t)i];
+        e[6] += A.epart[2 * (size_t)i + 1];
+        c0 += A.cpart[2 * (size_t)i];
+        c1 += A.cpart[2 * (size_t)i + 1];
+    }
+    for (int c = 0; c < 7; ++c) s_e[c][threadIdx.x] = e[c];
+    s_c[0][threadIdx.x] = c0;
+    s_c[1][threadIdx.x] = c1;
+    __syncthreads();
+    for (int o = NT / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            for (int c = 0; c < 7; ++c) s_e[c][threadIdx.x] += s_e[c][threadIdx.x + o];
+            s_c[0][threadIdx.x] += s_c[0][threadIdx.x + o];
+            s_c[1][threadIdx.x] += s_c[1][threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double total = 0;
+        for (int c = 0; c < 7; ++c) {      // MMFF94.java:390-392: sum in component order
+            const double v = convert_unit(s_e[c][0], A.unit_num, A.unit_den);
+            A.out[1 + c] = v;
+            total += v;
+        }
+        // a truncated survivor list means missing pairs: the total is poisoned (NaN) so that no caller - host or
+        // device side, before or after an all-reduce - can mistake the result for a valid energy
+        // bit 0: retry with longer lists, bit 1: density beyond the entry format, bit 2: non-finite coordinate
+        const int ovf = A.overflow ? ((A.overflow[0] ? 1 : 0) | (A.overflow[3] ? 2 : 0) | (A.overflow[1] ? 4 : 0)) : 0;
+        A.out[0] = ovf ? __longlong_as_double(0x7ff8000000000000ll) : total;
+        A.out[8] = (double)s_c[0][0];
+        A.out[9] = (double)s_c[1][0];
+        if (A.out_host) {
+            for (int c = 0; c < kOutHeader; ++c) A.out_host[c] = A.out[c];
+            A.out_host[kOutHeader] = (double)ovf;
+            __threadfence_system();
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kReduceWarps * 32)
@@ -585,51 +635,7 @@ reduce_kernel(ReduceArgs A) {
         }
         return;
     }
-    // last block: energies and pair counts, fixed-order strided sums + shared-memory tree
-    constexpr int NT = kReduceWarps * 32;
-    __shared__ double s_e[7][NT];
-    __shared__ unsigned long long s_c[2][NT];
-    double e[7] = {0, 0, 0, 0, 0, 0, 0};
-    unsigned long long c0 = 0, c1 = 0;
-    for (int i = threadIdx.x; i < A.n_bpart; i += NT)
-        for (int c = 0; c < 5; ++c) e[c] += A.bpart[5 * (size_t)i + c];
-    for (int i = threadIdx.x; i < A.n_epart; i += NT) {
-        e[5] += A.epart[2 * (size_t)i];
-        e[6] += A.epart[2 * (size_t)i + 1];
-        c0 += A.cpart[2 * (size_t)i];
-        c1 += A.cpart[2 * (size_t)i + 1];
-    }
-    for (int c = 0; c < 7; ++c) s_e[c][threadIdx.x] = e[c];
-    s_c[0][threadIdx.x] = c0;
-    s_c[1][threadIdx.x] = c1;
-    __syncthreads();
-    for (int o = NT / 2; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) {
-            for (int c = 0; c < 7; ++c) s_e[c][threadIdx.x] += s_e[c][threadIdx.x + o];
-            s_c[0][threadIdx.x] += s_c[0][threadIdx.x + o];
-            s_c[1][threadIdx.x] += s_c[1][threadIdx.x + o];
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        double total = 0;
-        for (int c = 0; c < 7; ++c) {      // MMFF94.java:390-392: sum in component order
-            const double v = convert_unit(s_e[c][0], A.unit_num, A.unit_den);
-            A.out[1 + c] = v;
-            total += v;
-        }
-        // a truncated survivor list means missing pairs: the total is poisoned (NaN) so that no caller - host or
-        // device side, before or after an all-reduce - can mistake the result for a valid energy
-        const int ovf = A.overflow ? *A.overflow : 0;
-        A.out[0] = ovf ? __longlong_as_double(0x7ff8000000000000ll) : total;
-        A.out[8] = (double)s_c[0][0];
-        A.out[9] = (double)s_c[1][0];
-        if (A.out_host) {
-            for (int c = 0; c < kOutHeader; ++c) A.out_host[c] = A.out[c];
-            A.out_host[kOutHeader] = (double)ovf;
-            __threadfence_system();
-        }
-    }
+    reduce_energy_block(A);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -188,7 +188,10 @@ class AdamMinimizer(EnergyMinimizer):
                     xyz[a, i] += distance
                     if self.constraint is None or self.constraint.check(self.forcefield, container) or not initialized:
                         difference = self._energy(container) - initialEnergy
-                        grads[a, i] = -difference / abs(distance)
+                        # Java double division (AdamMinimizer.java:96): a step that rounds to 0 gives +-Infinity / NaN
+                        # and the loop goes on
+                        with np.errstate(divide="ignore", invalid="ignore"):
+                            grads[a, i] = np.float64(-difference) / np.float64(abs(distance))
                         if not initialized:
                             xyz[a, i] += -distance
                         elif difference > 0:
