@@ -157,6 +157,13 @@ int64_t jme_eval_out_size(const jme_handle_t* h, int want_gradient);   /* double
 int jme_gd_minimize(jme_handle_t* h, int max_steps, double step_size, double threshold, double* xyz_inout,
                     int64_t* energy_calls, int* steps_done, double* step_energies, int capacity);
 
+/* AdamMinimizer.minimize (minimizer/AdamMinimizer.java:62-120, the AdamOptimizer of :132-161) restated the same
+ * way, no constraint: per coordinate one energy before the move, the Adam step, one energy after it, keep / undo.
+ * A step that rounds to zero gives an infinite or NaN slope exactly as the Java division does. */
+int jme_adam_minimize(jme_handle_t* h, int max_steps, double step_size, double threshold, double beta1, double beta2,
+                      double epsilon, double* xyz_inout, int64_t* energy_calls, int* steps_done, double* step_energies,
+                      int capacity);
+
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 uint64_t jme_launch_count(const jme_handle_t* h);
 

@@ -8,6 +8,6 @@ from .system import MolecularSystem, enumerate_terms, pair_separation  # noqa: F
 from .forcefield import (EnergyComponent, EnergyUnit, ForceField, JmeError, MMFF94,  # noqa: F401
                          measure_fp64_peak)
 from .minimizer import (AdamMinimizer, EnergyMinimizer, GradientDescentMinimizer,  # noqa: F401
-                        GradientMinimizer, NativeGradientDescentMinimizer)
+                        GradientMinimizer, NativeAdamMinimizer, NativeGradientDescentMinimizer)
 
 __version__ = "0.1.0"

@@ -21,7 +21,7 @@ EXPORTS = (
     "jme_energy", "jme_energy_gradient", "jme_pair_stats", "jme_pair_list", "jme_set_stream",
     "jme_set_coords_device", "jme_eval_device", "jme_eval_out_size", "jme_launch_count",
     "jme_measure_fp64_peak", "jme_enumerate_terms", "jme_exclusions", "jme_set_profiling", "jme_profile_read",
-    "jme_gd_minimize",
+    "jme_gd_minimize", "jme_adam_minimize",
 )
 
 _lib = None
@@ -88,6 +88,9 @@ def lib():
     L.jme_gd_minimize.restype = C.c_int
     L.jme_gd_minimize.argtypes = [H, C.c_int, C.c_double, C.c_double, c_f64p, C.POINTER(C.c_int64), C.POINTER(C.c_int),
                                   c_f64p, C.c_int]
+    L.jme_adam_minimize.restype = C.c_int
+    L.jme_adam_minimize.argtypes = [H, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, c_f64p,
+                                    C.POINTER(C.c_int64), C.POINTER(C.c_int), c_f64p, C.c_int]
     L.jme_enumerate_terms.restype = C.c_int
     L.jme_enumerate_terms.argtypes = [C.c_int64, c_i32p, c_u8p, C.c_int64, c_i32p, c_i32p,
                                       c_i32p, c_i64p, c_i32p, c_i64p, c_i32p, c_i64p]

@@ -373,17 +373,19 @@ cudaEvent_t* prof_slot(jme_handle* h) {
     return &h->prof_events[3 * h->prof_used];
 }
 
-size_t ap_smem_bytes(const DeviceSystem& ds) {
-    return (size_t)ds.n_types * ds.n_types * sizeof(PairConst) + kApWarps * (4 * 32 + 16) * sizeof(double) +
+constexpr size_t kTableSmemLimit = 48 * 1024;       // larger type-pair tables stay in global memory
+
+size_t ap_smem_bytes(const DeviceSystem& ds, bool tsm) {
+    return (tsm ? (size_t)ds.n_types * ds.n_types * sizeof(PairConst) : 0) + kApWarps * (4 * 32 + 16) * sizeof(double) +
            kApWarps * (kNI * 3 + 3) * 32 * sizeof(double);
 }
 
-template <bool GRAD, bool CUTOFF, int KSPLIT>
-int launch_ap_k(jme_handle* h) {
+template <bool GRAD, bool CUTOFF, int KSPLIT, bool TSM>
+int launch_ap_kt(jme_handle* h) {
     const int n_items = h->item_end - h->item_begin;
     if (n_items <= 0) return JME_OK;
-    const size_t smem = ap_smem_bytes(h->ds);
-    auto kern = ap_kernel<GRAD, CUTOFF, KSPLIT>;
+    const size_t smem = ap_smem_bytes(h->ds, TSM);
+    auto kern = ap_kernel<GRAD, CUTOFF, KSPLIT, TSM>;
     if (smem > 48 * 1024) JME_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = KSPLIT == 1 ? (n_items + kApWarps - 1) / kApWarps : n_items;
     kern<<<grid, kApThreads, smem, h->stream>>>(h->ds, h->d_items, h->item_begin, h->item_end, h->d_tile_mask, h->d_masks,
@@ -391,6 +393,12 @@ int launch_ap_k(jme_handle* h) {
     ++h->launches;
     JME_CUDA(h, cudaGetLastError());
     return JME_OK;
+}
+
+template <bool GRAD, bool CUTOFF, int KSPLIT>
+int launch_ap_k(jme_handle* h) {
+    const bool tsm = (size_t)h->ds.n_types * h->ds.n_types * sizeof(PairConst) <= kTableSmemLimit;
+    return tsm ? launch_ap_kt<GRAD, CUTOFF, KSPLIT, true>(h) : launch_ap_kt<GRAD, CUTOFF, KSPLIT, false>(h);
 }
 
 // Small systems do not have enough tiles to fill the chip with one warp per item: let the four warps of a CTA
@@ -544,14 +552,27 @@ int grow_cell_lists(jme_handle* h) {
     const int cap = p.list_cap * 2;
     const size_t count = (size_t)std::max(1, h->ds.n) * cap;
     if (cap > (1 << 16)) { h->err = "survivor-list capacity limit"; return JME_ERR_NOMEM; }
-    dev_free(h, p.d_list);
-    p.d_list = nullptr;
-    int rc = dev_alloc(h, &p.d_list, count);
-    if (rc) {            // keep the plan usable at the old capacity
-        std::string why = h->err;
-        if (dev_alloc(h, &p.d_list, count / 2)) { p.built = false; h->plan_dirty = true; }
-        h->err = why;
-        return rc;
+    int rc;
+    if (p.cluster != 0) {
+        dev_free(h, p.d_clist);
+        p.d_clist = nullptr;
+        rc = dev_alloc(h, &p.d_clist, count);
+        if (rc) {            // keep the plan usable at the old capacity
+            std::string why = h->err;
+            if (dev_alloc(h, &p.d_clist, count / 2)) { p.built = false; h->plan_dirty = true; }
+            h->err = why;
+            return rc;
+        }
+    } else {
+        dev_free(h, p.d_list);
+        p.d_list = nullptr;
+        rc = dev_alloc(h, &p.d_list, count);
+        if (rc) {
+            std::string why = h->err;
+            if (dev_alloc(h, &p.d_list, count / 2)) { p.built = false; h->plan_dirty = true; }
+            h->err = why;
+            return rc;
+        }
     }
     p.list_cap = cap;
     JME_CUDA(h, cudaMemset(p.d_overflow, 0, sizeof(int)));
@@ -815,6 +836,71 @@ int jme_gd_minimize(jme_handle_t* h, int max_steps, double step_size, double thr
                 } else {
                     last_energy += difference;
                     g = g * 1.05;
+                }
+            }
+        if (!initialized) {
+            initialized = true;
+        } else {
+            ++step;
+            if (step_energies && n_log < capacity) step_energies[n_log++] = last_energy;
+        }
+    }
+    if (energy_calls) *energy_calls = calls;
+    if (steps_done) *steps_done = step;
+    return JME_OK;
+}
+
+int jme_adam_minimize(jme_handle_t* h, int max_steps, double step_size, double threshold, double beta1, double beta2,
+                      double epsilon, double* xyz, int64_t* energy_calls, int* steps_done, double* step_energies, int capacity) {
+    if (!h || !xyz) return JME_ERR_INVALID;
+    JME_CUDA(h, cudaSetDevice(h->device));
+    const int64_t n = h->hs.n;
+    int rc = jme_set_coords(h, xyz, n);
+    if (rc) return rc;
+    int64_t calls = 0;
+    auto energy = [&](double& e) -> int {
+        ++calls;
+        return eval_host(h, false, &e, nullptr, nullptr);
+    };
+    auto move = [&](int64_t a, int i, double d) -> int {          // movePoint, AdamMinimizer.java:122-130
+        xyz[3 * a + i] += d;
+        return jme_set_coord1(h, a, i, xyz[3 * a + i]);
+    };
+    struct Adam { double m = 0, v = 0; int t = 1; };              // AdamOptimizer, :132-161
+    std::vector<Adam> adams(3 * (size_t)n);
+    std::vector<double> grads(3 * (size_t)n, step_size);           // :63-70
+    int step = 0;
+    bool initialized = false;
+    double last_energy = 0, energy_per_step = 0;
+    if ((rc = energy(last_energy))) return rc;                     // :73
+    int n_log = 0;
+    if (step_energies && n_log < capacity) step_energies[n_log++] = last_energy;
+    while (step < max_steps) {
+        if (step != 0 && std::fabs(energy_per_step - last_energy) <= threshold) break;    // :78-80
+        energy_per_step = last_energy;
+        for (int64_t a = 0; a < n; ++a)
+            for (int i = 0; i < 3; ++i) {
+                double& g = grads[3 * a + i];
+                if (g == 0) continue;                              // :86-88
+                double initial;
+                if ((rc = energy(initial))) return rc;             // :89
+                Adam& o = adams[3 * a + i];
+                const double x = xyz[3 * a + i];
+                ++o.t;                                             // optimize(), :153-160
+                o.m = beta1 * o.m + (1 - beta1) * g;
+                o.v = beta2 * o.v + (1 - beta2) * g * g;
+                const double m_hat = o.m / (1 - std::pow(beta1, o.t));
+                const double v_hat = o.v / (1 - std::pow(beta2, o.t));
+                const double distance = (x - step_size * m_hat / (std::sqrt(v_hat) + epsilon)) - x;   // :90
+                if ((rc = move(a, i, distance))) return rc;
+                double e;
+                if ((rc = energy(e))) return rc;
+                const double difference = e - initial;             // :93
+                g = -difference / std::fabs(distance);             // :94 (a zero step gives +-inf / NaN, like Java)
+                if (!initialized || difference > 0) {
+                    if ((rc = move(a, i, -distance))) return rc;   // :95-99
+                } else {
+                    last_energy += difference;                     // :101
                 }
             }
         if (!initialized) {

@@ -59,6 +59,7 @@ struct GridParams {
 };
 
 struct alignas(32) PosQ { double x, y, z, q; };
+constexpr int kPadType = 0x80;          // stype of a padding record (cluster path): type 0, flag bit 7
 
 // entries of the survivor lists: sorted position of the partner in the low 24 bits, its type index above
 constexpr int kEntryBits = 24;
@@ -76,6 +77,8 @@ struct CellArrays {
     int pad;                 // every cell is padded to a multiple of `pad` sorted positions (1: no padding)
     int n_spad;              // capacity of the arrays indexed by sorted position: n + (pad - 1) * min(n, max_cells)
     int seg_target;          // wanted number of segments (cluster path), 0 otherwise
+    int ring;                // cluster path: slots per neighbour row of the force windows
+    unsigned int ring_magic; // floor(2^32 / ring)
     int* flags;              // [4] device flags: [0] list overflow, [1] non-finite coordinate, [2] window fallback used
     int* cell_of;            // [n] cell index per original atom
     int* count;              // [max_cells + 1]
@@ -309,9 +312,11 @@ __global__ void cell_rank_gather_kernel(DeviceSystem S, CellArrays C) {
         for (int q = b + m; q < e; ++q) {
             C.orig[q] = -1;
             C.scell[q] = c;
-            PosQ f; f.x = f.y = f.z = 1e100; f.q = 0.0;
+            // padding: never listed as a partner (NaN in the FP32 copy); as a member of a cluster it is switched off
+            // by the flag bit of its type, and it sits on a real atom of the cell so that nothing overflows
+            PosQ f; f.x = x; f.y = y; f.z = z; f.q = 0.0;
             C.spq[q] = f;
-            C.stype[q] = 0;
+            C.stype[q] = kPadType;
             C.fxyz[q] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, __int_as_float(0));
         }
     }
@@ -837,10 +842,12 @@ struct CellPlan {
     int sms = 148;
     int cl_warps = 0, cl_table_in_smem = 1;
     size_t cl_smem_grad = 0, cl_smem_energy = 0;
+    uint2* d_clist = nullptr;      // cluster lists: [clusters][list_cap] 64-bit entries
     double* d_gi = nullptr;
     double* d_gj = nullptr;
     double* d_gj_ovf = nullptr;
     int* d_excl_src = nullptr;
+    uint2* d_cellmask = nullptr;   // [max_cells] which force slots were written for a cell (cl_cellmask_kernel)
     std::vector<void*> new_allocs;
 
     std::vector<void*> take_new_allocs() { std::vector<void*> v; v.swap(new_allocs); return v; }
@@ -887,7 +894,7 @@ inline int build_cell_plan(CellPlan& p, const HostSystem& hs, const DeviceSystem
         a.n_spad = p.n_spad = n + (a.pad - 1) * std::min(n, a.max_cells);
         a.bbox_blocks = std::max(1, std::min(592, (n + 255) / 256));
         const int scan_blocks = (a.max_cells + 1 + kScanBlock - 1) / kScanBlock;
-        const size_t ns = (size_t)p.n_spad + 1;          // + 1: see the gather of cl_pair_kernel
+        const size_t ns = (size_t)p.n_spad + 64;         // spare elements: the gather of cl_pair_kernel, cl_pitch
         bool ok = cell_alloc(p, &a.grid, 1, err) && cell_alloc(p, &a.cell_of, n, err) && cell_alloc(p, &a.count, a.max_cells + 1, err) &&
                   cell_alloc(p, &a.start, a.max_cells + 1, err) && cell_alloc(p, &a.cursor, a.max_cells, err) &&
                   cell_alloc(p, &a.block_sums, scan_blocks, err) && cell_alloc(p, &a.order_tmp, ns, err) &&
@@ -931,12 +938,14 @@ inline int build_cell_plan(CellPlan& p, const HostSystem& hs, const DeviceSystem
             p.n_epart = p.epart_cap = a.max_cells;
             if (!cell_alloc(p, &p.d_epart, 2 * (size_t)p.n_epart, err) || !cell_alloc(p, &p.d_cpart, 2 * (size_t)p.n_epart, err)) return JME_ERR_NOMEM;
             // cluster lists: one per cluster (every cluster holds at least one atom: <= n clusters)
-            p.list_cap = 512;
-            while (p.list_cap > 128 && (size_t)n * p.list_cap * sizeof(unsigned int) > ((size_t)16 << 30)) p.list_cap /= 2;
-            if (!cell_alloc(p, &p.d_list, (size_t)std::max(1, n) * p.list_cap, err) || !cell_alloc(p, &p.d_count, std::max(1, n), err) ||
+            p.list_cap = 384;
+            while (p.list_cap > 128 && (size_t)n * p.list_cap * sizeof(uint2) > ((size_t)24 << 30)) p.list_cap -= 64;
+            if (!cell_alloc(p, &p.d_clist, (size_t)std::max(1, n) * p.list_cap, err) || !cell_alloc(p, &p.d_count, std::max(1, n), err) ||
                 !cell_alloc(p, &p.d_gi, 3 * ns, err) || !cell_alloc(p, &p.d_gj, (size_t)2 * 13 * 3 * ns, err) ||
-                !cell_alloc(p, &p.d_gj_ovf, 3 * ns, err) || !cell_alloc(p, &p.d_excl_src, hs.excl_ent.size(), err))
+                !cell_alloc(p, &p.d_gj_ovf, 3 * ns, err) || !cell_alloc(p, &p.d_excl_src, hs.excl_ent.size(), err) ||
+                !cell_alloc(p, &p.d_cellmask, (size_t)a.max_cells, err))
                 return JME_ERR_NOMEM;
+            cudaMemset(p.d_gj_ovf, 0, 3 * ns * sizeof(double));      // the reduction leaves it zero again after every use
             std::vector<int> src(hs.excl_ent.size());
             for (int64_t i = 0; i < hs.n; ++i)
                 for (int64_t e = hs.excl_ptr[i]; e < hs.excl_ptr[i + 1]; ++e) src[(size_t)e] = (int)i;

@@ -7,14 +7,14 @@
 //
 //   sort        (jme_cells.cuh) cell edge = cutoff / 2, atoms sorted by cell (z, y, x), rank inside a cell by original
 //               index; every cell is padded to a multiple of C sorted positions, so CLUSTERS of C consecutive
-//               positions never straddle a cell.  Padding records sit far away and never pass a distance test.
+//               positions never straddle a cell.  Padding records are never listed and are switched off as members.
 //   cl_list     FP32, conservative: per cluster the list of partner ATOMS j later in the sorted order (the half
 //               shell: the rest of the own cell row, then the rows dy > 0 and dz > 0) that are inside the padded
-//               cutoff of at least one atom of the cluster.  One 32-bit entry per (cluster, j):
-//               [ position of j relative to the row's window | row of the half shell | type of j | C excluded bits
-//               | C one-four bits ].
-//   cl_mark     one thread per exclusion entry: finds the pair's list entry (binary search, entries are sorted) and
-//               sets the excluded / 1-4 bit of the atom, so the FP64 kernel needs no exclusion lookup at all.
+//               cutoff of at least one atom of the cluster.  One 64-bit entry per (cluster, j), everything the FP64
+//               kernel needs precomputed: { sorted position of j | slot of j in the force window, type of j, C
+//               "pair excluded" bits, C "1-4 pair" bits }.
+//   cl_mark     one thread per exclusion entry: finds the pair's list entry (binary search, entries are sorted by
+//               position) and sets the excluded / 1-4 bit of the atom, so the FP64 kernel needs no exclusion lookup.
 //   cl_pair     FP64.  A warp sweeps a SEGMENT (<= 12 consecutive cells of one cell row) cluster by cluster; a lane
 //               takes 4 / C list entries per trip and evaluates them against the C atoms of the cluster = 4
 //               independent FP64 chains per lane (what the FP64 pipe needs).  The exact
@@ -25,34 +25,38 @@
 //               cell and slides along x with the sweep: a cell that leaves the window is flushed to its slot array
 //               (coalesced), so a j-atom receives exactly one partial per (row of the half shell, segment) - no
 //               atomics, every partial has one writer and the final sum a fixed order => bit-reproducible.
-//   cl_reduce   per atom: i-side sum + the <= 26 j-side slots that were written for its cell (derived from the grid,
-//               nothing stored) + bonded slots; unit conversion; scatter to the caller's atom order.
+//               Entries and partner records travel through registers: entries two trips ahead (their cache lines
+//               are prefetched to L2 a whole cluster ahead), records one trip ahead.
+//   cl_reduce   per cell: which of the <= 26 j-side slots were written for it follows from the grid (nothing is
+//               stored); per atom: i-side sum + those slots + bonded slots; unit conversion; scatter to the
+//               caller's atom order.
 #pragma once
 
 #include "jme_cells.cuh"
 
 namespace jme {
 
-constexpr int kClRing = 128;          // window slots (atoms) per neighbour row and warp; power of two
 constexpr int kClMaxRows = 13;        // rows of the half shell at reach 2
 constexpr int kClMaxSegLen = 12;      // cells per segment (GridParams::seg_len is clamped to this in grid_setup_kernel)
-constexpr int kClRowPitch = 16;       // row-info entries per cell
+constexpr int kClRowPitch = 16;       // row-table entries per cell
 constexpr int kClBatch = 32;          // clusters staged per batch
-constexpr int kClMaxWarps = 5;        // warps per CTA of the gradient kernel (one CTA per SM: the windows fill shared memory)
-constexpr int kClEnergyWarps = 8;     // energy-only kernel (no windows)
+constexpr int kClWarps = 8;           // warps per CTA, one CTA per SM (255 registers per thread)
+constexpr int kClMaxRing = 128;       // upper bound of the window slots per neighbour row (11 slot bits: 13 * 128 + 1)
+
+// 64-bit list entry: .x = sorted position of the partner, .y = meta
+constexpr int kMetaSlotBits = 11;                               // window slot: row * ring + ring index; 13 * ring = dummy slot
+constexpr unsigned int kMetaSlotMask = (1u << kMetaSlotBits) - 1u;
+constexpr int kMetaTypeShift = 11;                              // 7 bits
+constexpr unsigned int kMetaOvf = 1u << 18;                     // the partner does not fit the ring of its row here: atomics
+constexpr int kMetaExclShift = 24;                              // C bits: pair (atom a of the cluster, partner) does not count
+constexpr int kMetaF14Shift = 28;                               // C bits: ... is a 1-4 pair
 
 template <int C>
 struct ClFmt {
-    static_assert(C == 1 || C == 2 || C == 4, "cluster size");
+    static_assert(C == 2 || C == 4, "cluster size");
     static constexpr int kK = 4 / C;                               // list entries per lane per trip: C * kK = 4 chains
     static constexpr int kSpan = 32 * kK;                          // entries per trip
-    static constexpr int kRelBits = (32 - 2 * C - 11) < 16 ? (32 - 2 * C - 11) : 16;
-    static constexpr unsigned int kRelMask = (1u << kRelBits) - 1u;
-    static constexpr int kRowShift = kRelBits;                     // 4 bits: row of the half shell
-    static constexpr int kTypeShift = kRelBits + 4;                // 7 bits: type index of j
-    static constexpr unsigned int kKeyMask = (1u << (kRelBits + 4)) - 1u;   // (row, rel): entries are sorted by it
-    static constexpr int kExclShift = 32 - 2 * C;                  // C bits: pair (atom a of the cluster, j) is excluded
-    static constexpr int kF14Shift = 32 - C;                       // C bits: ... is a 1-4 pair
+    static constexpr unsigned int kAllExcl = ((1u << C) - 1u) << kMetaExclShift;
 };
 
 // half-shell row o -> (dy, dz):  o = 0 own row; 1..reach: dz = 0, dy = o; then dz = 1..reach, dy = -reach..reach
@@ -71,28 +75,50 @@ __device__ __forceinline__ int cl_row_index(int dy, int dz, int reach) {       /
 __device__ __forceinline__ int cl_seg_first_cell(const GridParams& g, long long s) {
     return s >= g.n_seg ? g.ncell : (int)(s / g.nsx) * g.nx + (int)(s % g.nsx) * g.seg_len;
 }
+// pitch (in positions) of the per-position force arrays: the number of sorted positions of THIS evaluation (known on
+// the device only), not the worst case they are allocated for - the slot arrays then lie a few MB apart instead of
+// 16 large pages apart, which spreads them over the TLB sets
+__device__ __forceinline__ size_t cl_pitch(int n_sorted) { return ((size_t)n_sorted + 63) / 32 * 32; }
+// t mod ring for 0 <= t < 2^31 without a division: magic = floor(2^32 / ring) underestimates the quotient by at most 1
+__device__ __forceinline__ int cl_ring_mod(int t, int ring, unsigned int magic) {
+    int r = t - (int)__umulhi((unsigned int)t, magic) * ring;
+    return r >= ring ? r - ring : r;
+}
 
 // ---- cluster lists -----------------------------------------------------------------------------------
 struct ClListArgs {
-    unsigned int* list;            // [clusters][cap]
+    uint2* list;                   // [clusters][cap]
     int* count;                    // [clusters]
     int cap;
     int parts;                     // warps sharing one cell (small systems)
     int rank, world;
+    int ring;                      // window slots per neighbour row (the evaluation kernel's shared-memory budget)
+    unsigned int ring_magic;       // floor(2^32 / ring)
 };
 
+// if (pred) base[index] = v (8 bytes), as a predicated streaming store with a single-instruction address
+__device__ __forceinline__ void st_cs_if64(bool pred, unsigned long long base, unsigned int index, uint2 v) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 a;\n\tsetp.ne.u32 p, %0, 0;\n\tmad.wide.u32 a, %1, 8, %2;\n\t"
+                 "@p st.global.cs.v2.u32 [a], {%3, %4};\n\t}"
+                 ::"r"((unsigned int)pred), "r"(index), "l"(base), "r"(v.x), "r"(v.y) : "memory");
+}
+
+constexpr int kClListMinBlocks = 3;   // 85 registers per thread: no spills
+
 template <int C>
-__global__ void __launch_bounds__(kListThreads, JME_LIST_MIN_BLOCKS)
+__global__ void __launch_bounds__(kListThreads, kClListMinBlocks)
 cl_list_kernel(CellArrays A, ClListArgs P) {
     using F = ClFmt<C>;
     __shared__ float2 s_fi[kListWarps][32][4];  // atom il as (x,x) (y,y) (z,z) -: operands of the packed FP32 test
     __shared__ int s_jb[kListWarps][16];        // first candidate of half-shell row o
-    __shared__ int s_cw[kListWarps][16];        // first position of row o's window (entries are relative to it)
+    __shared__ int s_cw[kListWarps][16];        // first position of row o's window for this cell
+    __shared__ int s_p0[kListWarps][16];        // ring origin of row o: first position of its window for the SEGMENT
     __shared__ int s_off[kListWarps][17];       // exclusive prefix of the candidate counts (virtual candidate index)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float2 (*fis)[4] = s_fi[warp];
     int* jbs = s_jb[warp];
     int* cws = s_cw[warp];
+    int* p0s = s_p0[warp];
     int* off = s_off[warp];
     const GridParams g = *A.grid;
     const unsigned int lt_mask = (1u << lane) - 1u;
@@ -115,11 +141,12 @@ cl_list_kernel(CellArrays A, ClListArgs P) {
         const int k0 = part * per, k1 = min(nclu, k0 + per);
         if (k0 >= k1) continue;
         const int cx = c % g.nx, cy = (c / g.nx) % g.ny, cz = c / (g.nx * g.ny);
+        const int xa = cx / g.seg_len * g.seg_len;                   // first cell of the segment that sweeps this cell
         const int a_begin = c0 + C * k0, a_end = c0 + C * k1;        // sorted positions of this item's clusters
         int total;
         {   // candidate range of half-shell row `lane` and the prefix sums that flatten the <= 13 ranges into one
             // virtual index space, so that every trip has all its slots filled
-            int jb = 0, len = 0, cw = 0;
+            int jb = 0, len = 0, cw = 0, p0 = 0;
             if (lane < H) {
                 int dy, dz;
                 cl_row_offset(lane, g.reach, dy, dz);
@@ -128,6 +155,7 @@ cl_list_kernel(CellArrays A, ClListArgs P) {
                     const int x0 = max(cx - g.reach, 0), x1 = min(cx + g.reach, g.nx - 1);
                     const int row = (z2 * g.ny + y2) * g.nx;
                     cw = A.start[row + x0];
+                    p0 = A.start[row + max(xa - g.reach, 0)];
                     // own row: only partners later in the sorted order than the first atom of the first cluster
                     jb = lane == 0 ? a_begin + 1 : cw;
                     len = A.start[row + x1 + 1] - jb;
@@ -141,7 +169,7 @@ cl_list_kernel(CellArrays A, ClListArgs P) {
             }
             total = __shfl_sync(0xffffffffu, incl, 31);
             __syncwarp();
-            if (lane < 16) { jbs[lane] = jb; cws[lane] = cw; off[lane] = incl - len; }
+            if (lane < 16) { jbs[lane] = jb; cws[lane] = cw; p0s[lane] = p0; off[lane] = incl - len; }
             if (lane == 16) off[16] = incl - len;                     // = total for lane >= H (len == 0)
         }
         for (int ch = a_begin; ch < a_end; ch += 32) {              // at most 32 atoms (32 / C clusters) at a time
@@ -163,7 +191,7 @@ cl_list_kernel(CellArrays A, ClListArgs P) {
             for (int k = 0; k < kListK; ++k) r[k] = 0;
             for (int vb = 0; vb < total; vb += 32 * kListK) {
                 float ax[kListK], ay[kListK], az[kListK];
-                unsigned int en[kListK];
+                unsigned int meta[kListK];
                 int jj[kListK];
 #pragma unroll
                 for (int k = 0; k < kListK; ++k) {
@@ -175,10 +203,11 @@ cl_list_kernel(CellArrays A, ClListArgs P) {
                     ax[k] = valid ? a.x : qnan;                       // NaN never passes the distance test
                     ay[k] = a.y; az[k] = a.z;
                     jj[k] = j;
-                    const unsigned int rel = (unsigned int)(j - cws[r[k]]);
-                    if (valid && rel > F::kRelMask) A.flags[3] = 1;   // a row window with more atoms than the entry format holds
-                    en[k] = (rel & F::kRelMask) | ((unsigned int)r[k] << F::kRowShift) |
-                            ((unsigned int)__float_as_int(a.w) << F::kTypeShift);
+                    // the partner's slot in the force window of the sweeping warp: ring index counted from the ring
+                    // origin of its row; a partner further from the window start than the ring is long is flagged
+                    const int slot = r[k] * P.ring + cl_ring_mod(valid ? j - p0s[r[k]] : 0, P.ring, P.ring_magic);
+                    meta[k] = (unsigned int)slot | ((unsigned int)__float_as_int(a.w) << kMetaTypeShift) |
+                              (j - cws[r[k]] >= P.ring ? kMetaOvf : 0u);
                 }
                 unsigned long long px[kListK / 2], py[kListK / 2], pz[kListK / 2];
 #pragma unroll
@@ -221,7 +250,11 @@ cl_list_kernel(CellArrays A, ClListArgs P) {
                         unsigned int o = (unsigned int)(kq * P.cap + cnt);
 #pragma unroll
                         for (int k = 0; k < kListK; ++k) {
-                            st_cs_if(h[k], rows, o + __popc(m[k] & lt_mask), en[k]);
+                            // a partner inside the own cluster: the atoms a >= j - p0 do not come before it in the sorted
+                            // order - their pair bits are set as "excluded", the evaluation needs no order test
+                            const int dj = jj[k] - p0;
+                            const unsigned int own = dj < C ? ((((1u << C) - 1u) >> dj) << dj) << kMetaExclShift : 0u;
+                            st_cs_if64(h[k], rows, o + __popc(m[k] & lt_mask), make_uint2((unsigned int)jj[k], meta[k] | own));
                             o += __popc(m[k]);
                         }
                         if (lane == kq) my_cnt += tot;
@@ -233,69 +266,62 @@ cl_list_kernel(CellArrays A, ClListArgs P) {
             if (lane < nq) P.count[ch / C + lane] = my_cnt;
         }
     }
+    (void)F::kK;
 }
 
 // ---- exclusion / 1-4 bits ------------------------------------------------------------------------------
 // One thread per (directed) exclusion entry; the direction whose source atom comes first in the sorted order owns
-// the pair.  The partner's entry in the source cluster's list is found by binary search on (row, rel) - the list
+// the pair.  The partner's entry in the source cluster's list is found by binary search on the position - the list
 // kernel emits entries in that order - and the atom's excluded / 1-4 bit is OR-ed in.  Pairs beyond the cutoff have
 // no entry: nothing to mark.
 template <int C>
 __global__ void __launch_bounds__(256)
-cl_mark_kernel(CellArrays A, const int* __restrict__ excl_src, unsigned int* __restrict__ list, const int* __restrict__ count,
+cl_mark_kernel(CellArrays A, const int* __restrict__ excl_src, uint2* __restrict__ list, const int* __restrict__ count,
                int cap, int rank, int world) {
-    using F = ClFmt<C>;
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= A.n_excl_ent) return;
     const unsigned int x = A.sexcl_ent[k];
-    const int sj = (int)(x & ~kFlag14);
+    const unsigned int sj = x & ~kFlag14;
     const int si = A.sorted_of[excl_src[k]];
-    if (si >= sj) return;
+    if ((unsigned int)si >= sj) return;
     const GridParams& g = *A.grid;
-    const int ci = A.scell[si], cj = A.scell[sj];
     {
+        const int ci = A.scell[si];
         const long long s0 = (long long)g.n_seg * rank / world, s1 = (long long)g.n_seg * (rank + 1) / world;
         if (ci < cl_seg_first_cell(g, s0) || ci >= cl_seg_first_cell(g, s1)) return;      // not this shard's list
     }
-    const int nxy = g.nx * g.ny;
-    const int ix = ci % g.nx, iy = (ci / g.nx) % g.ny, iz = ci / nxy;
-    const int jx = cj % g.nx, jy = (cj / g.nx) % g.ny, jz = cj / nxy;
-    const int o = cl_row_index(jy - iy, jz - iz, g.reach);
-    if (o < 0 || jx - ix > g.reach || ix - jx > g.reach) return;
-    const int cw = A.start[(jz * g.ny + jy) * g.nx + max(ix - g.reach, 0)];
-    const unsigned int key = ((unsigned int)o << F::kRowShift) | (unsigned int)(sj - cw);
     const int q = si / C, a = si % C;
-    unsigned int* lst = list + (size_t)q * cap;
-    int lo = 0, hi = min(count[q], cap);
+    uint2* lst = list + (size_t)q * cap;
+    const int n = min(count[q], cap);
+    int lo = 0, hi = n;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if ((lst[mid] & F::kKeyMask) < key) lo = mid + 1; else hi = mid;
+        if (lst[mid].x < sj) lo = mid + 1; else hi = mid;
     }
-    if (lo < min(count[q], cap) && (lst[lo] & F::kKeyMask) == key)
-        atomicOr(&lst[lo], 1u << (((x & kFlag14) ? F::kF14Shift : F::kExclShift) + a));
+    if (lo < n && lst[lo].x == sj)
+        atomicOr(&lst[lo].y, 1u << (((x & kFlag14) ? kMetaF14Shift : kMetaExclShift) + a));
 }
 
 // ---- evaluation ----------------------------------------------------------------------------------------
 struct ClPairArgs {
-    const unsigned int* list;      // [clusters][cap]
+    const uint2* list;             // [clusters][cap]
     const int* count;              // [clusters]
     int cap;
     int rank, world;
+    int ring;                      // window slots per neighbour row
     int n_spad;                    // pitch of the per-position arrays below
-    double* gi;                    // [3][n_spad] i-side sums by sorted position
-    double* gj;                    // [2 * kClMaxRows][3][n_spad] j-side window flushes: slot 2 * row + (segment & 1)
-    double* gj_ovf;                // [3][n_spad] atomically accumulated contributions of atoms beyond a window's capacity
+    double* gi;                    // [position][3] i-side sums by sorted position
+    double* gj;                    // [2 * kClMaxRows][cl_pitch][3] j-side window flushes: slot 2 * row + (segment & 1)
+    double* gj_ovf;                // [position][3] atomically accumulated contributions of atoms beyond a window's capacity
     double* epart;                 // [n_seg][2] per-segment energies (vdw, ele)
     unsigned long long* cpart;     // [n_seg][2] pairs evaluated, candidate pairs
-    int table_in_smem;
     // pair-list emission (EMIT only)
     int* out_i; int* out_j; unsigned char* out_14; long long capacity; unsigned long long* cursor;
 };
 
 // sum of v[i] over the 32 lanes for N values at the cost of about N + log2(32 / N) shuffles instead of 5 N: in every
 // halving step a lane keeps one half of its values and hands the other half to its partner.  On return v[0] of lane
-// l holds the warp total of value  (l >> (5 - log2 N)) ... i.e. value i is complete in lane  i * (32 / N)  (and in
-// the lanes that differ from it in the low log2(32 / N) bits).
+// l holds the warp total of value  l / (32 / N).
 template <int N>
 __device__ __forceinline__ void warp_multi_sum(double (&v)[N], int lane) {
     static_assert(N == 1 || N == 2 || N == 4 || N == 8 || N == 16 || N == 32, "power of two");
@@ -313,49 +339,56 @@ __device__ __forceinline__ void warp_multi_sum(double (&v)[N], int lane) {
     for (; m > 0; m >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], m);
 }
 
-template <int C>
-struct ClNb {                      // what a lane holds of its ClFmt<C>::kK partners of one trip
-    unsigned int e[ClFmt<C>::kK];
-    PosQ p[ClFmt<C>::kK];
-};
-
-__host__ __device__ constexpr size_t cl_warp_smem(bool grad) {
-    return (grad ? (size_t)3 * kClMaxRows * kClRing * sizeof(double) : 0) + kRingSlots * kChunk * sizeof(unsigned int) +
-           kClMaxSegLen * kClRowPitch * sizeof(int2) + 2 * kClBatch * sizeof(int);
+// per-warp shared memory: the force window (3 planes of kClMaxRows * ring + 8 doubles: the extra ones hold the dummy
+// slot of lanes beyond the end of a list), the row table and the batch's cluster data
+__host__ __device__ constexpr size_t cl_window_plane(int ring) { return (size_t)kClMaxRows * ring + 8; }
+constexpr int kClNextBytes = 2 * (4 * 32 + 16);   // the current and the next cluster's atoms (C records + C types), ping-pong
+__host__ __device__ constexpr size_t cl_warp_smem(bool grad, int ring) {
+    return (grad ? 3 * cl_window_plane(ring) * sizeof(double) : 0) + kClMaxSegLen * kClRowPitch * sizeof(int) +
+           2 * kClBatch * sizeof(int) + kClNextBytes;
 }
 
-template <int C, bool GRAD, bool EMIT>
-__global__ void __launch_bounds__(32 * (GRAD ? kClMaxWarps : kClEnergyWarps), 1)
+__device__ __forceinline__ uint2 ld_entry(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// TSM: the type-pair table sits in shared memory (LDS.128); otherwise it is read through L1 / L2
+template <int C, bool GRAD, bool EMIT, bool TSM>
+__global__ void __launch_bounds__(32 * kClWarps, 1)
 cl_pair_kernel(DeviceSystem S, CellArrays A, ClPairArgs P) {
     using F = ClFmt<C>;
     constexpr int K = F::kK;
-    constexpr int R = kClRing;
     constexpr unsigned int FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int TT = S.n_types * S.n_types;
+    const int RING = P.ring;
+    const int plane = (int)cl_window_plane(RING);                // doubles between the x, y and z planes
     PairConst* s_table = reinterpret_cast<PairConst*>(smem_raw);
-    unsigned char* wbase = smem_raw + (P.table_in_smem ? (((size_t)TT * sizeof(PairConst) + 15) & ~(size_t)15) : 0) +
-                           (size_t)warp * cl_warp_smem(GRAD);
-    double* acc = reinterpret_cast<double*>(wbase);                                      // [3][kClMaxRows * R] (GRAD)
-    unsigned int* ring = reinterpret_cast<unsigned int*>(wbase + (GRAD ? (size_t)3 * kClMaxRows * R * sizeof(double) : 0));
-    int2* rowinfo = reinterpret_cast<int2*>(ring + kRingSlots * kChunk);                 // [cell of the segment][row]: {window start, window start - ring origin}
-    int* s_cnt = reinterpret_cast<int*>(rowinfo + kClMaxSegLen * kClRowPitch);           // list length of the batch's clusters
+    unsigned char* wbase = smem_raw + (TSM ? (((size_t)TT * sizeof(PairConst) + 15) & ~(size_t)15) : 0) +
+                           (size_t)warp * cl_warp_smem(GRAD, RING);
+    double* acc = reinterpret_cast<double*>(wbase);                                      // [3][plane] (GRAD)
+    int* rowtab = reinterpret_cast<int*>(wbase + (GRAD ? 3 * (size_t)plane * sizeof(double) : 0));   // [cell of the segment][row]: window start
+    int* s_cnt = rowtab + kClMaxSegLen * kClRowPitch;                                    // list length of the batch's clusters
     int* s_ci = s_cnt + kClBatch;                                                        // their cell (index inside the segment)
-    if (P.table_in_smem) {
+    uint4* s_next = reinterpret_cast<uint4*>(s_ci + kClBatch);                           // the next cluster's C records, then its C types
+    if (TSM) {
         for (int t = threadIdx.x; t < TT; t += blockDim.x) s_table[t] = S.table[t];
     }
     if (GRAD) {
-        for (int t = lane; t < 3 * kClMaxRows * R; t += 32) acc[t] = 0.0;                // flushes leave it zero again
+        for (int t = lane; t < 3 * plane; t += 32) acc[t] = 0.0;                         // flushes leave it zero again
     }
     __syncthreads();
-    const PairConst* table = P.table_in_smem ? s_table : S.table;
 
     const GridParams g = *A.grid;
     const int H = g.n_half;
     const PosQ* __restrict__ spq = A.spq;
     const long long s0 = (long long)g.n_seg * P.rank / P.world, s1 = (long long)g.n_seg * (P.rank + 1) / P.world;
-    constexpr int kAccPlane = kClMaxRows * R;                     // doubles between the x, y and z planes
+    const unsigned int dummy_meta = (unsigned int)(kClMaxRows * RING) | F::kAllExcl;    // lanes beyond the end of a list
+    const size_t np = cl_pitch(A.start[g.ncell]);                // positions per slot array (xyz interleaved)
 
     for (;;) {
         long long seg = 0;
@@ -385,12 +418,9 @@ cl_pair_kernel(DeviceSystem S, CellArrays A, ClPairArgs P) {
             }
             __syncwarp();
             for (int ci = 0; ci < xb - xa; ++ci) {
-                int2 v = make_int2(0, 0);
-                if (my_rowbase >= 0) {
-                    v.x = A.start[my_rowbase + max(xa + ci - g.reach, 0)];
-                    v.y = v.x - my_p0;
-                }
-                if (lane < kClRowPitch) rowinfo[ci * kClRowPitch + lane] = v;
+                int v = 0;
+                if (my_rowbase >= 0) v = A.start[my_rowbase + max(xa + ci - g.reach, 0)];
+                if (lane < kClRowPitch) rowtab[ci * kClRowPitch + lane] = v;
             }
             __syncwarp();
             const int slot_par = sx & 1;
@@ -401,21 +431,24 @@ cl_pair_kernel(DeviceSystem S, CellArrays A, ClPairArgs P) {
                     const int lo = __shfl_sync(FULL, my_lo, o);
                     const int hi = __shfl_sync(FULL, target, o);
                     const int p0 = __shfl_sync(FULL, my_p0, o);
-                    if (rb < 0) continue;
-                    double* dst = P.gj + (size_t)(2 * o + slot_par) * 3 * P.n_spad;
-                    for (int pos = lo + lane; pos < hi; pos += 32) {
-                        const bool in_ring = pos - lo < R;            // positions beyond the capacity were never accumulated here
-                        const int idx = o * R + ((pos - p0) & (R - 1));
+                    if (rb < 0 || hi <= lo) continue;
+                    double* dst = P.gj + ((size_t)(2 * o + slot_par) * np + lo) * 3;
+                    const int r0 = cl_ring_mod(lo - p0, RING, A.ring_magic);
+                    for (int d = lane; d < hi - lo; d += 32) {
+                        const bool in_ring = d < RING;                // positions beyond the capacity were never accumulated here
+                        int ri = r0 + d;
+                        if (ri >= RING) ri -= RING;
+                        const int idx = o * RING + ri;
                         double vx = 0, vy = 0, vz = 0;
                         if (in_ring) {
-                            vx = acc[idx]; vy = acc[kAccPlane + idx]; vz = acc[2 * kAccPlane + idx];
-                            acc[idx] = 0.0; acc[kAccPlane + idx] = 0.0; acc[2 * kAccPlane + idx] = 0.0;
+                            vx = acc[idx]; vy = acc[plane + idx]; vz = acc[2 * plane + idx];
+                            acc[idx] = 0.0; acc[plane + idx] = 0.0; acc[2 * plane + idx] = 0.0;
                         }
-                        dst[pos] = vx;
-                        dst[P.n_spad + pos] = vy;
-                        dst[2 * (size_t)P.n_spad + pos] = vz;
+                        dst[3 * d] = vx;
+                        dst[3 * d + 1] = vy;
+                        dst[3 * d + 2] = vz;
                     }
-                    if (lane == o) my_lo = max(my_lo, hi);
+                    if (lane == o) my_lo = hi;
                 }
                 __syncwarp();
             };
@@ -423,175 +456,218 @@ cl_pair_kernel(DeviceSystem S, CellArrays A, ClPairArgs P) {
 
             for (int qb = q0; qb < q1; qb += kClBatch) {
                 const int nq = min(kClBatch, q1 - qb);
-                __syncwarp();                                     // the previous batch's reads of the ring / s_cnt are over
+                __syncwarp();                                     // the previous batch's reads of s_cnt / s_ci are over
                 s_cnt[lane] = lane < nq ? min(P.count[qb + lane], P.cap) : 0;
                 s_ci[lane] = lane < nq ? A.scell[C * (qb + lane)] - rowbase - xa : 0;
                 __syncwarp();
-
-                // chunk requests run over the same (cluster, chunk) sequence as the trips, two chunks ahead
-                int q_il = 0, q_c = 0, q_slot = 0;
-                auto request = [&]() {
-                    if (q_il < nq) {
-                        const unsigned int* src = P.list + ((size_t)(qb + q_il) * P.cap + kChunk * q_c + 4 * lane);
-                        cp_async16(ring + q_slot * kChunk + 4 * lane, src);
-                        q_slot = q_slot == kRingSlots - 1 ? 0 : q_slot + 1;
-                        if (kChunk * (q_c + 1) < s_cnt[q_il]) ++q_c; else { ++q_il; q_c = 0; }
+                {   // the batch's first two lists on their way to L2
+                    const int n0 = s_cnt[0], n1 = nq > 1 ? s_cnt[1] : 0;
+                    if (16 * lane < n0) prefetch_l2(P.list + (size_t)qb * P.cap + 16 * lane);
+                    if (16 * lane < n1) prefetch_l2(P.list + (size_t)(qb + 1) * P.cap + 16 * lane);
+                }
+                // the stream of trips: (cluster, trip) of the trip being evaluated and of the two behind it in the
+                // software pipeline; every cluster has at least one trip (an empty list still writes its i-side zeros)
+                auto trips_of = [&](int il) { return max(1, (s_cnt[il] + F::kSpan - 1) / F::kSpan); };
+                auto load_entries = [&](int il, int t, uint2 (&E)[K]) {
+                    const uint2* src = P.list + (size_t)(qb + il) * P.cap + F::kSpan * t + lane;
+                    const int n = s_cnt[il];
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        E[k] = make_uint2((unsigned int)(C * (qb + il)), dummy_meta);
+                        if (F::kSpan * t + 32 * k + lane < n) E[k] = ld_entry(src + 32 * k);
                     }
-                    cp_async_commit();
                 };
-                request(); request(); request();
-                cp_async_wait<2>();
-                __syncwarp();
+                int il = 0, t = 0, T = trips_of(0);               // being evaluated
+                int il1 = 0, t1 = 0, T1 = T;                      // next trip (its records are gathered now)
+                int il2, t2, T2;                                  // the trip after it (its entries are loaded now)
+                auto advance = [&](int& i, int& tt, int& TT_) {
+                    if (tt + 1 < TT_) { ++tt; return; }
+                    ++i; tt = 0;
+                    TT_ = i < nq ? trips_of(i) : 1;
+                };
+                advance(il1, t1, T1);
+                il2 = il1; t2 = t1; T2 = T1;
+                advance(il2, t2, T2);
 
-                int il = 0, b = 0, slot = 0, ci = 0, n_hits = 0, ipos0 = 0;
-                double xi[C], yi[C], zi[C], qi2[C], gix[C], giy[C], giz[C];
-                const PairConst* trow[C];
-                PosQ nxt_p[C];
-                int nxt_t[C];
+                int ci = 0, ipos0 = 0;
+                double qi2[C], gix[C], giy[C], giz[C];
+                unsigned int trow[C];                             // byte offset of the atom's row of the type-pair table
+                unsigned int pad_excl = 0;                        // "excluded" bits of the cluster's padding atoms
+                // a cluster's atoms (C records of 32 bytes, C types) are fetched one cluster ahead by the first 2 C + 1
+                // lanes, 16 bytes each, and parked in shared memory: no register copies of them in the hot loop
+                auto fetch_cluster = [&](int q) -> uint4 {
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (lane < 2 * C) v = reinterpret_cast<const uint4*>(spq + (size_t)C * q)[lane];
+                    else if (lane < 2 * C + C) v.x = (unsigned int)A.stype[(size_t)C * q + (lane - 2 * C)];
+                    return v;
+                };
+                int cb = 0;                                       // buffer of the cluster being evaluated
+                auto park_cluster = [&](uint4 v) {                // into the other buffer
+                    uint4* dst = s_next + (cb ^ 1) * 9;
+                    if (lane < 2 * C) dst[lane] = v;
+                    else if (lane < 2 * C + C) reinterpret_cast<unsigned int*>(dst + 2 * C)[lane - 2 * C] = v.x;
+                };
+                uint4 nxt = fetch_cluster(qb);
+                bool nxt_pending = false;
+                __syncwarp();
+                park_cluster(nxt);
+                __syncwarp();
+                const double* cp = reinterpret_cast<const double*>(s_next);      // x, y, z, q of the cluster's atoms
 #pragma unroll
                 for (int a = 0; a < C; ++a) {
-                    nxt_p[a] = load_posq(spq + (size_t)C * qb + a);
-                    nxt_t[a] = A.stype[(size_t)C * qb + a];
-                    xi[a] = yi[a] = zi[a] = qi2[a] = gix[a] = giy[a] = giz[a] = 0.0;
-                    trow[a] = table;
+                    qi2[a] = gix[a] = giy[a] = giz[a] = 0.0;
+                    trow[a] = 0;
                 }
-
-                auto gather = [&](ClNb<C>& n, int k, unsigned int e, int cell) {
-                    n.e[k] = e;
-                    const int2 info = rowinfo[cell * kClRowPitch + ((e >> F::kRowShift) & 15u)];
-                    unsigned long long addr;
-                    asm("mad.wide.u32 %0, %1, 32, %2;" : "=l"(addr) : "r"((unsigned int)info.x + (e & F::kRelMask)), "l"(spq));
-                    n.p[k] = load_posq(reinterpret_cast<const PosQ*>(addr));
-                };
-                ClNb<C> NA, NB = {};
+                uint2 E0[K], E1[K];
+                PosQ GA[K], GB[K];
+                load_entries(0, 0, E0);
+                if (il1 < nq) load_entries(il1, t1, E1);
 #pragma unroll
-                for (int k = 0; k < K; ++k) gather(NA, k, 32 * k + lane < s_cnt[0] ? ring[32 * k + lane] : 0u, s_ci[0]);
+                for (int k = 0; k < K; ++k) GA[k] = load_posq(spq + E0[k].x);
 
-                auto trip = [&](const ClNb<C>& p, ClNb<C>& nx) -> bool {
-                    if (b == 0) {                             // a new cluster starts with this trip (warp-uniform)
-                        n_hits = s_cnt[il];
+                // one trip: E0 / G are this trip's entries and records, E1 the next trip's entries (its records go to Gn)
+                auto trip = [&](const PosQ (&G)[K], PosQ (&Gn)[K]) -> bool {
+                    if (nxt_pending) {                        // the atoms fetched during the previous trip go to their parking place
+                        __syncwarp();
+                        park_cluster(nxt);
+                        nxt_pending = false;
+                        __syncwarp();
+                    }
+                    if (t == 0) {                             // a new cluster starts with this trip (warp-uniform)
                         ipos0 = C * (qb + il);
                         const int ci_new = s_ci[il];
+                        pad_excl = 0;
+                        cb ^= 1;                              // the parked cluster becomes the current one
+                        cp = reinterpret_cast<const double*>(s_next + cb * 9);
+                        const int* nt = reinterpret_cast<const int*>(s_next + cb * 9 + 2 * C);
 #pragma unroll
                         for (int a = 0; a < C; ++a) {
-                            xi[a] = nxt_p[a].x; yi[a] = nxt_p[a].y; zi[a] = nxt_p[a].z;
-                            qi2[a] = 2.0 * S.ele_scale * nxt_p[a].q;             // doubled energies, see pair_terms
-                            trow[a] = table + nxt_t[a] * S.n_types;
+                            qi2[a] = 2.0 * S.ele_scale * cp[4 * a + 3];          // doubled energies, see pair_terms
+                            const int ty = nt[a];
+                            trow[a] = (unsigned int)((ty & 0x7f) * S.n_types * (int)sizeof(PairConst));
+                            if (ty & kPadType) pad_excl |= 1u << (kMetaExclShift + a);
                             gix[a] = giy[a] = giz[a] = 0.0;
                         }
                         if (GRAD && ci_new != cur_ci) {       // the sweep moves on: cells that left the windows are flushed
                             int target = 0;
-                            if (lane < kClRowPitch) target = rowinfo[ci_new * kClRowPitch + lane].x;
+                            if (lane < kClRowPitch) target = rowtab[ci_new * kClRowPitch + lane];
                             flush_to(target);
                             cur_ci = ci_new;
                         }
                         ci = ci_new;
                         if (il + 1 < nq) {                    // the next cluster's atoms, one cluster ahead
-#pragma unroll
-                            for (int a = 0; a < C; ++a) {
-                                nxt_p[a] = load_posq(spq + (size_t)C * (qb + il + 1) + a);
-                                nxt_t[a] = A.stype[(size_t)C * (qb + il + 1) + a];
-                            }
+                            nxt = fetch_cluster(qb + il + 1);
+                            nxt_pending = true;
                         }
-                        n_cand_w += (unsigned long long)n_hits * C;
+                        if (il + 2 < nq && 16 * lane < s_cnt[il + 2])      // and the list after the next one towards L2
+                            prefetch_l2(P.list + (size_t)(qb + il + 2) * P.cap + 16 * lane);
+                        n_cand_w += (unsigned long long)s_cnt[il] * C;
                     }
-                    int jpos[K], ridx[K], rel[K];
                     double dx[K][C], dy[K][C], dz[K][C], r2[K][C];
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
-                        const unsigned int e = p.e[k];
-                        const int o = (int)((e >> F::kRowShift) & 15u);
-                        const int2 info = rowinfo[ci * kClRowPitch + o];
-                        rel[k] = (int)(e & F::kRelMask);
-                        jpos[k] = info.x + rel[k];
-                        ridx[k] = o * R + ((info.y + rel[k]) & (R - 1));
 #pragma unroll
                         for (int a = 0; a < C; ++a) {
-                            dx[k][a] = xi[a] - p.p[k].x; dy[k][a] = yi[a] - p.p[k].y; dz[k][a] = zi[a] - p.p[k].z;
+                            // (the cluster's coordinates stay in shared memory: broadcast loads, 24 registers less)
+                            dx[k][a] = cp[4 * a] - G[k].x; dy[k][a] = cp[4 * a + 1] - G[k].y; dz[k][a] = cp[4 * a + 2] - G[k].z;
                             // strict double, left-to-right, no FMA: Point3d.distance squared
                             r2[k][a] = __dadd_rn(__dadd_rn(__dmul_rn(dx[k][a], dx[k][a]), __dmul_rn(dy[k][a], dy[k][a])),
                                                  __dmul_rn(dz[k][a], dz[k][a]));
                         }
                     }
-                    // next position of the stream; entering a chunk = its copy has landed, the slot two behind is reused
-                    const bool last = b + F::kSpan >= n_hits;
-                    int il2 = il, b2 = b + F::kSpan, slot2 = slot;
-                    if (last) { il2 = il + 1; b2 = 0; }
-                    if (last || (b2 & (kChunk - 1)) == 0) {
-                        slot2 = slot == kRingSlots - 1 ? 0 : slot + 1;
-                        __syncwarp();
-                        request();
-                        cp_async_wait<2>();
-                        __syncwarp();
-                    }
-                    if (il2 < nq) {
-                        const int hits2 = last ? s_cnt[il2] : n_hits;
-                        const int ci2 = last ? s_ci[il2] : ci;
-                        const unsigned int* src = ring + slot2 * kChunk + (b2 & (kChunk - 1)) + lane;
+                    // the pipeline: records of the next trip, entries of the one after it
+                    if (il1 < nq) {
 #pragma unroll
                         for (int k = 0; k < K; ++k) {
-                            unsigned int e = b2 + 32 * k + lane < hits2 ? src[32 * k] : 0u;
                             // the address carries a (never taken, for non-negative r2) dependence on r2, so that this load
-                            // is issued after the wait for this trip's operands and not before it.  A NaN r2 with the sign
-                            // bit set moves the index by one row bit at most: it stays inside the row table, and the
-                            // result is NaN anyway
-                            e ^= ((unsigned int)__double2hiint(r2[k][0]) >> 31) << F::kRowShift;
-                            gather(nx, k, e, ci2);
+                            // is issued after the wait for this trip's operands and not before it (a NaN r2 with the sign
+                            // bit set moves the index by one: the arrays have a spare element, the result is NaN anyway)
+                            unsigned long long addr;
+                            asm("mad.wide.u32 %0, %1, 32, %2;" : "=l"(addr)
+                                : "r"(E1[k].x + ((unsigned int)__double2hiint(r2[k][0]) >> 31)), "l"(spq));
+                            Gn[k] = load_posq(reinterpret_cast<const PosQ*>(addr));
                         }
                     }
-                    // arithmetic: K x C independent chains.  A pair that does not count (beyond the cutoff, excluded, not
-                    // later in the sorted order, padding) is evaluated at r2 = 1 with zero prefactors: exact zeros
+                    uint2 E2[K];
 #pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const unsigned int e = p.e[k];
-                        const bool valid = b + 32 * k + lane < n_hits;
-                        const int tj = (int)((e >> F::kTypeShift) & 127u);
-                        double gjx = 0, gjy = 0, gjz = 0;
+                    for (int k = 0; k < K; ++k) E2[k] = make_uint2(0u, dummy_meta);
+                    if (il2 < nq) load_entries(il2, t2, E2);
+                    // arithmetic: K x C independent chains, interleaved statement by statement (pair_terms_n).  A pair that
+                    // does not count (beyond the cutoff, excluded, not later in the sorted order, padding, a lane beyond
+                    // the end of the list) has its two prefactors set to zero: r2 is clamped away from 0 and bounded by the
+                    // list construction, so every intermediate is finite and the products are exact zeros
+                    {
+                        constexpr int NC = K * C;
+                        double r2c[NC], qq2[NC], e1[NC], e2v[NC], f[NC];
+                        PairConst pc[NC];
+                        unsigned int em[K];
 #pragma unroll
-                        for (int a = 0; a < C; ++a) {
-                            const bool on = valid && jpos[k] > ipos0 + a && !(r2[k][a] > S.r2_max) && !((e >> (F::kExclShift + a)) & 1u);
-                            const bool f14 = (e >> (F::kF14Shift + a)) & 1u;
-                            if (on) ++n_eval;
-                            if (EMIT) {
-                                if (on) {
-                                    const int oi = A.orig[ipos0 + a], oj = A.orig[jpos[k]];
-                                    const unsigned long long q = atomicAdd(P.cursor, 1ull);
-                                    if ((long long)q < P.capacity) { P.out_i[q] = min(oi, oj); P.out_j[q] = max(oi, oj); P.out_14[q] = f14; }
+                        for (int k = 0; k < K; ++k) {
+                            em[k] = E0[k].y | pad_excl;
+                            const unsigned int tj = ((em[k] >> kMetaTypeShift) & 127u) * (unsigned int)sizeof(PairConst);
+#pragma unroll
+                            for (int a = 0; a < C; ++a) {
+                                const int c = k * C + a;
+                                const bool on = !(r2[k][a] > S.r2_max) && !((em[k] >> (kMetaExclShift + a)) & 1u);
+                                const bool f14 = (em[k] >> (kMetaF14Shift + a)) & 1u;
+                                if (on) ++n_eval;
+                                if (EMIT) {
+                                    if (on) {
+                                        const int oi = A.orig[ipos0 + a], oj = A.orig[E0[k].x];
+                                        const unsigned long long q = atomicAdd(P.cursor, 1ull);
+                                        if ((long long)q < P.capacity) { P.out_i[q] = min(oi, oj); P.out_j[q] = max(oi, oj); P.out_14[q] = f14; }
+                                    }
                                 }
-                            } else {
-                                PairConst pc = trow[a][tj];
-                                pc.k1 = on ? pc.k1 : 0.0;
-                                const double qq2 = on ? (qi2[a] * p.p[k].q) * (f14 ? kEle14 : 1.0) : 0.0;
-                                double e1, e2v, f;
-                                pair_terms<GRAD>(on ? clamp_r2(r2[k][a]) : 1.0, pc, qq2, e1, e2v, f);
-                                ev += e1;
-                                ee += e2v;
-                                if (GRAD) {
-                                    gix[a] = fma(f, dx[k][a], gix[a]);
-                                    giy[a] = fma(f, dy[k][a], giy[a]);
-                                    giz[a] = fma(f, dz[k][a], giz[a]);
-                                    gjx = fma(-f, dx[k][a], gjx);
-                                    gjy = fma(-f, dy[k][a], gjy);
-                                    gjz = fma(-f, dz[k][a], gjz);
-                                }
+                                if (TSM) pc[c] = *reinterpret_cast<const PairConst*>(smem_raw + trow[a] + tj);
+                                else pc[c] = *reinterpret_cast<const PairConst*>(reinterpret_cast<const unsigned char*>(S.table) + trow[a] + tj);
+                                pc[c].k1 = on ? pc[c].k1 : 0.0;
+                                // 0, 1 or 0.75 (1-4 pairs) as the high word of a double whose low word is zero
+                                const double sc = __hiloint2double(on ? (f14 ? 0x3fe80000 : 0x3ff00000) : 0, 0);
+                                qq2[c] = (qi2[a] * G[k].q) * sc;
+                                r2c[c] = clamp_r2(r2[k][a]);
                             }
                         }
-                        if (GRAD && !EMIT && valid) {
-                            if (rel[k] < R) {                     // inside the window: plain read-modify-write, this warp is the only writer
-                                acc[ridx[k]] += gjx;
-                                acc[kAccPlane + ridx[k]] += gjy;
-                                acc[2 * kAccPlane + ridx[k]] += gjz;
-                            } else {                              // a row window denser than its capacity: atomics (order not fixed)
-                                atomicAdd(P.gj_ovf + jpos[k], gjx);
-                                atomicAdd(P.gj_ovf + P.n_spad + jpos[k], gjy);
-                                atomicAdd(P.gj_ovf + 2 * (size_t)P.n_spad + jpos[k], gjz);
-                                A.flags[2] = 1;
+                        if (!EMIT) {
+                            pair_terms_n<GRAD, NC>(r2c, pc, qq2, e1, e2v, f);
+#pragma unroll
+                            for (int c = 0; c < NC; ++c) { ev += e1[c]; ee += e2v[c]; }
+                        }
+                        if (GRAD && !EMIT) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) {
+                                double gjx = 0, gjy = 0, gjz = 0;
+#pragma unroll
+                                for (int a = 0; a < C; ++a) {
+                                    const int c = k * C + a;
+                                    gix[a] = fma(f[c], dx[k][a], gix[a]);
+                                    giy[a] = fma(f[c], dy[k][a], giy[a]);
+                                    giz[a] = fma(f[c], dz[k][a], giz[a]);
+                                    gjx = fma(-f[c], dx[k][a], gjx);
+                                    gjy = fma(-f[c], dy[k][a], gjy);
+                                    gjz = fma(-f[c], dz[k][a], gjz);
+                                }
+                                // the partner's window slot: plain read-modify-write - this warp is the only writer and the
+                                // partners of one trip are distinct (lanes beyond the list add 0 to the dummy slot)
+                                int ri = (int)(em[k] & kMetaSlotMask);
+                                if (__any_sync(FULL, (em[k] & kMetaOvf) != 0)) {  // rare: a row window denser than its ring
+                                    if (em[k] & kMetaOvf) {                       // atomics (order not fixed)
+                                        atomicAdd(P.gj_ovf + 3 * (size_t)E0[k].x, gjx);
+                                        atomicAdd(P.gj_ovf + 3 * (size_t)E0[k].x + 1, gjy);
+                                        atomicAdd(P.gj_ovf + 3 * (size_t)E0[k].x + 2, gjz);
+                                        A.flags[2] = 1;
+                                        ri = kClMaxRows * RING;                   // and nothing to the window
+                                        gjx = gjy = gjz = 0.0;
+                                    }
+                                }
+                                acc[ri] += gjx;
+                                acc[plane + ri] += gjy;
+                                acc[2 * plane + ri] += gjz;
                             }
                         }
                     }
                     __syncwarp();                                 // window updates of this trip before those of the next
-                    if (last && GRAD && !EMIT) {                  // the cluster is complete: reduce its i-side sums over the warp
-                        constexpr int NV = C == 1 ? 4 : (C == 2 ? 8 : 16);
+                    if (t + 1 == T && GRAD && !EMIT) {            // the cluster is complete: reduce its i-side sums over the warp
+                        constexpr int NV = C == 2 ? 8 : 16;
                         double v[NV];
 #pragma unroll
                         for (int i = 0; i < NV; ++i) v[i] = 0.0;
@@ -600,16 +676,21 @@ cl_pair_kernel(DeviceSystem S, CellArrays A, ClPairArgs P) {
                         warp_multi_sum<NV>(v, lane);
                         const int vi = lane / (32 / NV);          // value completed in this lane
                         if ((lane & (32 / NV - 1)) == 0 && vi < 3 * C)
-                            P.gi[(size_t)(vi % 3) * P.n_spad + ipos0 + vi / 3] = v[0];
+                            P.gi[3 * (size_t)ipos0 + vi] = v[0];
                     }
-                    il = il2; b = b2; slot = slot2;
+                    // shift the pipeline by one trip
+                    il = il1; t = t1; T = T1;
+                    il1 = il2; t1 = t2; T1 = T2;
+                    advance(il2, t2, T2);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) { E0[k] = E1[k]; E1[k] = E2[k]; }
                     return il < nq;
                 };
                 while (true) {
-                    if (!trip(NA, NB)) break;
-                    if (!trip(NB, NA)) break;
+                    if (!trip(GA, GB)) break;
+                    if (!trip(GB, GA)) break;
                 }
-                cp_async_wait<0>();
+                (void)ci;
             }
             {   // the segment is done: everything still in the windows goes out
                 int target = 0;
@@ -629,7 +710,6 @@ cl_pair_kernel(DeviceSystem S, CellArrays A, ClPairArgs P) {
             }
         }
     }
-    (void)n_warps;
 }
 
 // ---- final reduction of the cluster path ------------------------------------------------------------------
@@ -638,71 +718,104 @@ struct ClReduceArgs {
     int rank, world;
     const double* gi;
     const double* gj;
-    const double* gj_ovf;
+    double* gj_ovf;
+    const uint2* cellmask;         // [cells] cl_cellmask_kernel
     ReduceArgs R;                  // bonded slots, energy partials, units, outputs (gpart / direct unused)
 };
+
+// Which slots were written for a cell depends on the cell only: one thread per cell works that out
+// (mask.x: bit o = slot 2 o + (sa & 1) holds a flush of half-shell row o, bit 29 = sa & 1, bit 30 = sb & 1, bit 31 = the
+// cell's own segment belongs to this shard; mask.y: the same for the second writer sb), then one thread per sorted
+// position sums them.
+__global__ void __launch_bounds__(256)
+cl_cellmask_kernel(CellArrays A, int rank, int world, uint2* __restrict__ mask) {
+    const GridParams& g = *A.grid;
+    const long long s0 = (long long)g.n_seg * rank / world, s1 = (long long)g.n_seg * (rank + 1) / world;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < g.ncell; c += gridDim.x * blockDim.x) {
+        if (A.count[c] == 0) { mask[c] = make_uint2(0u, 0u); continue; }
+        const int cx = c % g.nx, cy = (c / g.nx) % g.ny, cz = c / (g.nx * g.ny);
+        // the segments of an i-row whose windows covered this cell - cells [xa - reach, xb - 1 + reach] - are sa and
+        // sb (at most two, of different parity); row o of the half shell belongs to the i-row (cy - dy, cz - dz)
+        const int sa = max(cx - g.reach, 0) / g.seg_len, sb = min((cx + g.reach) / g.seg_len, g.nsx - 1);
+        unsigned int ma = 0, mb = 0;
+        for (int o = 0; o < g.n_half; ++o) {
+            int dy, dz;
+            cl_row_offset(o, g.reach, dy, dz);
+            const int yi = cy - dy, zi = cz - dz;
+            if (yi < 0 || yi >= g.ny || zi < 0) continue;
+            const int irow = zi * g.ny + yi;
+            auto wrote = [&](int sx) {       // in this shard and holding at least one atom
+                const long long seg = (long long)irow * g.nsx + sx;
+                if (seg < s0 || seg >= s1) return false;
+                const int xa = sx * g.seg_len, xb = min(xa + g.seg_len, g.nx);
+                return A.start[irow * g.nx + xb] != A.start[irow * g.nx + xa];
+            };
+            if (wrote(sa)) ma |= 1u << o;
+            if (sb != sa && wrote(sb)) mb |= 1u << o;
+        }
+        const long long own_seg = (long long)(cz * g.ny + cy) * g.nsx + cx / g.seg_len;
+        if (own_seg >= s0 && own_seg < s1) ma |= 1u << 31;
+        ma |= (unsigned int)(sa & 1) << 29 | (unsigned int)(sb & 1) << 30;
+        mask[c] = make_uint2(ma, mb);
+    }
+}
 
 __global__ void __launch_bounds__(kReduceWarps * 32)
 cl_reduce_kernel(CellArrays A, ClReduceArgs Q) {
     const GridParams& g = *A.grid;
     if (blockIdx.x == gridDim.x - 1) {
         // last block: energies and pair counts over this shard's segments
-        ReduceArgs R = Q.R;
         const long long s0 = (long long)g.n_seg * Q.rank / Q.world, s1 = (long long)g.n_seg * (Q.rank + 1) / Q.world;
+        ReduceArgs R = Q.R;
         R.epart += 2 * s0; R.cpart += 2 * s0; R.n_epart = (int)(s1 - s0);
         R.overflow = A.flags;
         reduce_energy_block(R);
         return;
     }
     if (!Q.R.want_grad) return;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= A.start[g.ncell]) return;
-    const int a = A.orig[p];
-    if (a < 0) return;                                            // padding
-    const int c = A.scell[p];
-    const int cx = c % g.nx, cy = (c / g.nx) % g.ny, cz = c / (g.nx * g.ny);
-    const long long s0 = (long long)g.n_seg * Q.rank / Q.world, s1 = (long long)g.n_seg * (Q.rank + 1) / Q.world;
-    double gx = 0, gy = 0, gz = 0;
-    {   // i-side: written by the segment that holds the atom's cell
-        const long long seg = (long long)(cz * g.ny + cy) * g.nsx + cx / g.seg_len;
-        if (seg >= s0 && seg < s1) {
-            gx = Q.gi[p]; gy = Q.gi[Q.n_spad + p]; gz = Q.gi[2 * (size_t)Q.n_spad + p];
-        }
-    }
-    // j-side: for every row o of the half shell, the segments of the i-row (cy - dy, cz - dz) whose windows covered
-    // this cell - cells [xa - reach, xb - 1 + reach] - wrote slot 2 o + (segment & 1), provided they hold any atom
-    for (int o = 0; o < g.n_half; ++o) {
-        int dy, dz;
-        cl_row_offset(o, g.reach, dy, dz);
-        const int yi = cy - dy, zi = cz - dz;
-        if (yi < 0 || yi >= g.ny || zi < 0) continue;
-        const int irow = zi * g.ny + yi;
-        const int sa = max(cx - g.reach, 0) / g.seg_len, sb = min((cx + g.reach) / g.seg_len, g.nsx - 1);
-        for (int sx = sa; sx <= sb; ++sx) {
-            const long long seg = (long long)irow * g.nsx + sx;
-            if (seg < s0 || seg >= s1) continue;
-            const int xa = sx * g.seg_len, xb = min(xa + g.seg_len, g.nx);
-            if (A.start[irow * g.nx + xb] == A.start[irow * g.nx + xa]) continue;       // empty segment: wrote nothing
-            const double* src = Q.gj + (size_t)(2 * o + (sx & 1)) * 3 * Q.n_spad;
-            gx += src[p]; gy += src[Q.n_spad + p]; gz += src[2 * (size_t)Q.n_spad + p];
-        }
-    }
-    if (A.flags[2]) {
-        gx += Q.gj_ovf[p]; gy += Q.gj_ovf[Q.n_spad + p]; gz += Q.gj_ovf[2 * (size_t)Q.n_spad + p];
-    }
     const ReduceArgs& R = Q.R;
-    for (long long e = R.slot_ptr[a]; e < R.slot_ptr[a + 1]; ++e) {
-        const long long s = R.slot_idx[e];
-        if (s >= R.slot_lo && s < R.slot_hi) {
-            gx += R.slots[3 * s];
-            gy += R.slots[3 * s + 1];
-            gz += R.slots[3 * s + 2];
+    const bool use_ovf = A.flags[2] != 0;
+    const int n_sorted = A.start[g.ncell];
+    const size_t np = cl_pitch(n_sorted);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_sorted; p += (gridDim.x - 1) * blockDim.x) {
+        const int a = A.orig[p];
+        if (a < 0) continue;                                      // padding
+        const uint2 m = Q.cellmask[A.scell[p]];
+        const unsigned int pa = (m.x >> 29) & 1u, pb = (m.x >> 30) & 1u;
+        double gx = 0, gy = 0, gz = 0;
+        if (m.x >> 31) { gx = Q.gi[3 * (size_t)p]; gy = Q.gi[3 * (size_t)p + 1]; gz = Q.gi[3 * (size_t)p + 2]; }
+        // the slot loads of an atom are independent: issue them together (predicated), then sum in row order
+        double vx[kClMaxRows], vy[kClMaxRows], vz[kClMaxRows];
+#pragma unroll
+        for (int o = 0; o < kClMaxRows; ++o) {
+            const double* src = Q.gj + ((size_t)(2 * o + pa) * np + p) * 3;
+            const bool u = (m.x >> o) & 1u;
+            vx[o] = u ? src[0] : 0.0; vy[o] = u ? src[1] : 0.0; vz[o] = u ? src[2] : 0.0;
         }
+#pragma unroll
+        for (int o = 0; o < kClMaxRows; ++o) { gx += vx[o]; gy += vy[o]; gz += vz[o]; }
+        for (unsigned int v = m.y & 0x1fffu; v; v &= v - 1) {     // cells next to a segment boundary: the second writer
+            const double* src = Q.gj + ((size_t)(2 * (__ffs(v) - 1) + pb) * np + p) * 3;
+            gx += src[0]; gy += src[1]; gz += src[2];
+        }
+        if (use_ovf) {       // (and back to zero for the next evaluation)
+            double* ov = Q.gj_ovf + 3 * (size_t)p;
+            gx += ov[0]; gy += ov[1]; gz += ov[2];
+            ov[0] = 0.0; ov[1] = 0.0; ov[2] = 0.0;
+        }
+        for (long long e = R.slot_ptr[a]; e < R.slot_ptr[a + 1]; ++e) {
+            const long long sl = R.slot_idx[e];
+            if (sl >= R.slot_lo && sl < R.slot_hi) {
+                gx += R.slots[3 * sl];
+                gy += R.slots[3 * sl + 1];
+                gz += R.slots[3 * sl + 2];
+            }
+        }
+        double* o = R.out + kOutHeader + 3 * (size_t)a;
+        o[0] = convert_unit(gx, R.unit_num, R.unit_den);
+        o[1] = convert_unit(gy, R.unit_num, R.unit_den);
+        o[2] = convert_unit(gz, R.unit_num, R.unit_den);
     }
-    double* o = R.out + kOutHeader + 3 * (size_t)a;
-    o[0] = convert_unit(gx, R.unit_num, R.unit_den);
-    o[1] = convert_unit(gy, R.unit_num, R.unit_den);
-    o[2] = convert_unit(gz, R.unit_num, R.unit_den);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
@@ -713,28 +826,36 @@ inline int cl_configure(CellPlan& p, const DeviceSystem& ds, std::string& err) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const size_t table = (((size_t)ds.n_types * ds.n_types * sizeof(PairConst)) + 15) & ~(size_t)15;
-    p.cl_table_in_smem = table <= 64 * 1024 ? 1 : 0;
+    p.cl_table_in_smem = table <= 48 * 1024 ? 1 : 0;
     const size_t tb = p.cl_table_in_smem ? table : 0;
-    p.cl_warps = (int)std::min<size_t>(kClMaxWarps, ((size_t)max_smem - tb) / cl_warp_smem(true));
-    if (p.cl_warps < 1) { err = "cell path: not enough shared memory for one force window"; return JME_ERR_UNSUPPORTED; }
-    p.cl_smem_grad = tb + p.cl_warps * cl_warp_smem(true);
-    p.cl_smem_energy = tb + kClEnergyWarps * cl_warp_smem(false);
-    // about four segments per resident warp of the gradient kernel
-    p.arr.seg_target = 4 * p.sms * p.cl_warps;
+    // the ring length of the force windows from what kClWarps warps leave of the shared memory
+    const long long per_warp = ((long long)max_smem - (long long)tb) / kClWarps;
+    long long ring = (per_warp - (long long)cl_warp_smem(true, 0)) / (3 * kClMaxRows * (long long)sizeof(double));
+    ring = std::min<long long>(kClMaxRing, ring / 8 * 8);
+    if (ring < 32) { err = "cell path: not enough shared memory for the force windows"; return JME_ERR_UNSUPPORTED; }
+    p.arr.ring = (int)ring;
+    p.arr.ring_magic = (unsigned int)(0x100000000ull / (unsigned long long)ring);
+    p.cl_warps = kClWarps;
+    p.cl_smem_grad = tb + kClWarps * cl_warp_smem(true, (int)ring);
+    p.cl_smem_energy = tb + kClWarps * cl_warp_smem(false, (int)ring);
+    // about four segments per resident warp
+    p.arr.seg_target = 4 * p.sms * kClWarps;
     return JME_OK;
 }
 
 template <int C>
 inline int cl_run_lists_t(CellPlan& p, const DeviceSystem& ds, cudaStream_t st, uint64_t& launches, std::string& err) {
     ClListArgs A{};
-    A.list = p.d_list; A.count = p.d_count; A.cap = p.list_cap; A.rank = p.rank; A.world = p.world;
-    const long long resident = (long long)p.grid_list * kListWarps;
+    A.list = p.d_clist; A.count = p.d_count; A.cap = p.list_cap; A.rank = p.rank; A.world = p.world;
+    A.ring = p.arr.ring; A.ring_magic = p.arr.ring_magic;
+    const int grid = p.sms * kClListMinBlocks;
+    const long long resident = (long long)grid * kListWarps;
     A.parts = (int)std::max(1ll, std::min(8ll, 2 * resident * 12 / std::max(1, ds.n)));
     cudaMemsetAsync(p.arr.work_ctr, 0, 2 * sizeof(int), st);
-    cl_list_kernel<C><<<p.grid_list, kListThreads, 0, st>>>(p.arr, A);
+    cl_list_kernel<C><<<grid, kListThreads, 0, st>>>(p.arr, A);
     ++launches;
     if (p.arr.n_excl_ent > 0) {
-        cl_mark_kernel<C><<<(unsigned int)((p.arr.n_excl_ent + 255) / 256), 256, 0, st>>>(p.arr, p.d_excl_src, p.d_list, p.d_count,
+        cl_mark_kernel<C><<<(unsigned int)((p.arr.n_excl_ent + 255) / 256), 256, 0, st>>>(p.arr, p.d_excl_src, p.d_clist, p.d_count,
                                                                                         p.list_cap, p.rank, p.world);
         ++launches;
     }
@@ -748,26 +869,30 @@ inline int cl_run_lists(CellPlan& p, const DeviceSystem& ds, cudaStream_t st, ui
 }
 
 inline void cl_fill_pair_args(CellPlan& p, ClPairArgs& P) {
-    P.list = p.d_list; P.count = p.d_count; P.cap = p.list_cap;
-    P.rank = p.rank; P.world = p.world; P.n_spad = p.n_spad + 1;
+    P.list = p.d_clist; P.count = p.d_count; P.cap = p.list_cap;
+    P.rank = p.rank; P.world = p.world; P.n_spad = p.n_spad + 1; P.ring = p.arr.ring;
     P.gi = p.d_gi; P.gj = p.d_gj; P.gj_ovf = p.d_gj_ovf;
     P.epart = p.d_epart; P.cpart = p.d_cpart;
-    P.table_in_smem = p.cl_table_in_smem;
 }
 
-template <int C, bool GRAD, bool EMIT>
-inline int cl_launch_pairs(CellPlan& p, const DeviceSystem& ds, const ClPairArgs& P, cudaStream_t st, std::string& err) {
-    auto k = cl_pair_kernel<C, GRAD, EMIT>;
+template <int C, bool GRAD, bool EMIT, bool TSM>
+inline int cl_launch_pairs_t(CellPlan& p, const DeviceSystem& ds, const ClPairArgs& P, cudaStream_t st, std::string& err) {
+    auto k = cl_pair_kernel<C, GRAD, EMIT, TSM>;
     const size_t smem = GRAD ? p.cl_smem_grad : p.cl_smem_energy;
-    const int warps = GRAD ? p.cl_warps : kClEnergyWarps;
+    const int warps = kClWarps;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { err = std::string("cell path: shared memory request refused: ") + cudaGetErrorString(e); return JME_ERR_CUDA; }
     }
-    const int grid = GRAD ? p.sms : 2 * p.sms;
-    k<<<grid, 32 * warps, smem, st>>>(ds, p.arr, P);
+    k<<<p.sms, 32 * warps, smem, st>>>(ds, p.arr, P);
     JME_CELL_CHECK();
     return JME_OK;
+}
+
+template <int C, bool GRAD, bool EMIT>
+inline int cl_launch_pairs(CellPlan& p, const DeviceSystem& ds, const ClPairArgs& P, cudaStream_t st, std::string& err) {
+    return p.cl_table_in_smem ? cl_launch_pairs_t<C, GRAD, EMIT, true>(p, ds, P, st, err)
+                              : cl_launch_pairs_t<C, GRAD, EMIT, false>(p, ds, P, st, err);
 }
 
 inline int cl_run_pairs(CellPlan& p, const DeviceSystem& ds, bool grad, cudaStream_t st, uint64_t& launches, std::string& err) {
@@ -775,7 +900,6 @@ inline int cl_run_pairs(CellPlan& p, const DeviceSystem& ds, bool grad, cudaStre
     ClPairArgs P{};
     cl_fill_pair_args(p, P);
     cudaMemsetAsync(p.arr.work_ctr + 1, 0, sizeof(int), st);
-    if (grad) cudaMemsetAsync(p.d_gj_ovf, 0, 3 * (size_t)(p.n_spad + 1) * sizeof(double), st);
     ++launches;
     if (p.cluster == 2) return grad ? cl_launch_pairs<2, true, false>(p, ds, P, st, err) : cl_launch_pairs<2, false, false>(p, ds, P, st, err);
     return grad ? cl_launch_pairs<4, true, false>(p, ds, P, st, err) : cl_launch_pairs<4, false, false>(p, ds, P, st, err);
@@ -785,10 +909,15 @@ inline int cl_run_pairs(CellPlan& p, const DeviceSystem& ds, bool grad, cudaStre
 inline int cl_run_reduce(CellPlan& p, const DeviceSystem& ds, const ReduceArgs& R, cudaStream_t st, uint64_t& launches, std::string& err) {
     ClReduceArgs Q{};
     Q.n_spad = p.n_spad + 1; Q.rank = p.rank; Q.world = p.world;
-    Q.gi = p.d_gi; Q.gj = p.d_gj; Q.gj_ovf = p.d_gj_ovf;
+    Q.gi = p.d_gi; Q.gj = p.d_gj; Q.gj_ovf = p.d_gj_ovf; Q.cellmask = p.d_cellmask;
     Q.R = R;
     const int nt = kReduceWarps * 32;
-    const int grid = (R.want_grad ? (p.n_spad + nt - 1) / nt : 0) + 1;
+    if (R.want_grad) {
+        cl_cellmask_kernel<<<std::max(1, std::min(4 * p.sms, (ds.n + 255) / 256)), 256, 0, st>>>(p.arr, p.rank, p.world, p.d_cellmask);
+        ++launches;
+    }
+    // gradient: a grid-stride loop over the sorted positions (their number is only known on the device)
+    const int grid = (R.want_grad ? std::max(1, std::min(16 * p.sms, (ds.n + nt - 1) / nt)) : 0) + 1;
     cl_reduce_kernel<<<grid, nt, 0, st>>>(p.arr, Q);
     ++launches;
     JME_CELL_CHECK();

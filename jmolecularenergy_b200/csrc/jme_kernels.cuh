@@ -167,7 +167,9 @@ __device__ __forceinline__ void ap_tile(ApLaneState& L, const double* __restrict
 // KSPLIT = 4: the four warps of the CTA share ONE item and each takes a quarter of the 32 steps of every tile
 //             (small systems: 4x more parallelism per tile); the partial sums of the four warps are combined in
 //             shared memory in a fixed order, so the outputs are the same buffers as for KSPLIT = 1.
-template <bool GRAD, bool CUTOFF, int KSPLIT>
+// TSM: the type-pair table is staged in shared memory; a table too large for that (about 40+ atom types) is read through
+// the cache hierarchy instead
+template <bool GRAD, bool CUTOFF, int KSPLIT, bool TSM>
 __global__ void __launch_bounds__(kApThreads, 2)
 ap_kernel(DeviceSystem S, const ApItem* __restrict__ items, int item_begin, int item_end,
           const int* __restrict__ tile_mask, const TileMask* __restrict__ masks, int n_super,
@@ -177,7 +179,7 @@ ap_kernel(DeviceSystem S, const ApItem* __restrict__ items, int item_begin, int 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // shared: pair table, per-warp j staging (x, y, z, q: 4 x 32 doubles; type: 32 ints), KSPLIT combine area
     PairConst* s_table = reinterpret_cast<PairConst*>(smem_raw);
-    const int TT = S.n_types * S.n_types;
+    const int TT = TSM ? S.n_types * S.n_types : 0;
     double* s_stage = reinterpret_cast<double*>(s_table + TT);
     double* s_comb = s_stage + kApWarps * (4 * 32 + 16);       // [warps][kNI*3 + 3][32] (KSPLIT > 1 only)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -202,7 +204,7 @@ ap_kernel(DeviceSystem S, const ApItem* __restrict__ items, int item_begin, int 
         const int ia = (it.S * kNI + a) * kTile + lane;
         L.xi[a] = S.x[ia]; L.yi[a] = S.y[ia]; L.zi[a] = S.z[ia];
         L.qi2[a] = 2.0 * S.ele_scale * S.q[ia];             // doubled energies, see pair_terms
-        L.trow[a] = s_table + S.type[ia] * S.n_types;
+        L.trow[a] = (TSM ? s_table : S.table) + S.type[ia] * S.n_types;
         L.gix[a] = L.giy[a] = L.giz[a] = 0.0;
     }
     double ev = 0, ee = 0;

@@ -55,7 +55,7 @@ JME_HD double clamp1(double n) { return n > 1 ? 1 : (n < -1 ? -1 : n); }     // 
 // so that  2 E_vdw = 2 eps (1.07R/(r+0.07R))^7 (1.12R^7/(r^7+0.12R^7) - 2) = k1 s^-7 (c3/t - 2)
 // with s = r + c2, t = r^7 + c4.
 // ---------------------------------------------------------------------------------------------
-struct PairConst {
+struct alignas(16) PairConst {      // two 128-bit loads
     double k1, c2, c3, c4;
 };
 
@@ -129,6 +129,101 @@ JME_HD void pair_terms(double r2, const PairConst& pc, double qq2, double& e2_vd
         f_over_r = -(g * hrinv);
     } else {
         f_over_r = 0.0;
+    }
+}
+
+// The same arithmetic for N independent pairs, written statement by statement across the pairs: the N dependency
+// chains reach the assembler already interleaved, which is what the FP64 pipe wants (one warp instruction per two
+// cycles, eight cycles of dependent latency) when few warps are resident.  Bit-identical to N calls of pair_terms.
+template <bool GRAD, int N>
+JME_HD void pair_terms_n(const double (&r2)[N], const PairConst (&pc)[N], const double (&qq2)[N],
+                         double (&e2_vdw)[N], double (&e2_ele)[N], double (&f_over_r)[N]) {
+    double r[N], hrinv[N];
+#if defined(__CUDA_ARCH__)
+    double y[N], t0[N], e0[N], p0[N], q0[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(r2[i]));
+#pragma unroll
+    for (int i = 0; i < N; ++i) t0[i] = r2[i] * y[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) e0[i] = fma(-t0[i], y[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < N; ++i) p0[i] = fma(0.375, e0[i], 0.5);
+#pragma unroll
+    for (int i = 0; i < N; ++i) q0[i] = e0[i] * p0[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = fma(y[i], q0[i], y[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) r[i] = r2[i] * y[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) hrinv[i] = 0.5 * y[i];
+#else
+    for (int i = 0; i < N; ++i) { r[i] = sqrt(r2[i]); hrinv[i] = 0.5 / r[i]; }
+#endif
+    double s[N], u[N], r4[N], r6[N], t[N], st[N], x[N], iq[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) s[i] = r[i] + pc[i].c2;
+#pragma unroll
+    for (int i = 0; i < N; ++i) u[i] = r[i] + kEleBuf;
+#pragma unroll
+    for (int i = 0; i < N; ++i) r4[i] = r2[i] * r2[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) r6[i] = r4[i] * r2[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) t[i] = fma(r6[i], r[i], pc[i].c4);
+#pragma unroll
+    for (int i = 0; i < N; ++i) st[i] = s[i] * t[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = st[i] * u[i];
+#if defined(__CUDA_ARCH__)
+    {
+        double e1[N], q1[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(iq[i]) : "d"(x[i]));
+#pragma unroll
+        for (int i = 0; i < N; ++i) e1[i] = fma(-x[i], iq[i], 1.0);
+#pragma unroll
+        for (int i = 0; i < N; ++i) q1[i] = fma(e1[i], e1[i], e1[i]);
+#pragma unroll
+        for (int i = 0; i < N; ++i) iq[i] = fma(iq[i], q1[i], iq[i]);
+    }
+#else
+    for (int i = 0; i < N; ++i) iq[i] = 1.0 / x[i];
+#endif
+    double iu[N], ist[N], is[N], it[N], is2[N], is4[N], is7[N], w[N], b[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) iu[i] = iq[i] * st[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) ist[i] = iq[i] * u[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) is[i] = ist[i] * t[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) it[i] = ist[i] * s[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) is2[i] = is[i] * is[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) is4[i] = is2[i] * is2[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) is7[i] = is4[i] * is2[i] * is[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) w[i] = pc[i].k1 * is7[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) b[i] = pc[i].c3 * it[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) e2_vdw[i] = w[i] * (b[i] - 2.0);
+#pragma unroll
+    for (int i = 0; i < N; ++i) e2_ele[i] = qq2[i] * iu[i];
+    if (GRAD) {
+        double d[N], g[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) d[i] = fma(w[i], (b[i] * r6[i]) * it[i], e2_vdw[i] * is[i]);
+#pragma unroll
+        for (int i = 0; i < N; ++i) g[i] = fma(7.0, d[i], e2_ele[i] * iu[i]);
+#pragma unroll
+        for (int i = 0; i < N; ++i) f_over_r[i] = -(g[i] * hrinv[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) f_over_r[i] = 0.0;
     }
 }
 

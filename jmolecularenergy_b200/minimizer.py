@@ -208,6 +208,39 @@ class AdamMinimizer(EnergyMinimizer):
                     self.onStepConsumer(self.step, lastCalculatedEnergy)
 
 
+class NativeAdamMinimizer(EnergyMinimizer):
+    """:class:`AdamMinimizer`'s loop run inside ``libjme_b200.so`` (``jme_adam_minimize``); no constraints."""
+
+    def __init__(self, forceField, beta1: float, beta2: float, epsilon: float):
+        super().__init__()
+        self.forcefield = forceField
+        self.beta1, self.beta2, self.epsilon = beta1, beta2, epsilon
+        self.energyCalls = 0
+        self.stepEnergies = []
+
+    def minimize(self, container, maximumSteps: int, stepSize: float, threshold: float) -> None:
+        import ctypes as C
+        if self.constraint is not None:
+            raise NotImplementedError("constraints are evaluated on the host: use AdamMinimizer")
+        st = self.forcefield._state(container)
+        st.sync_options(self.forcefield, self.forcefield.path)
+        xyz = np.ascontiguousarray(container.xyz, dtype=np.float64)
+        calls, steps = C.c_int64(), C.c_int()
+        log = np.zeros(maximumSteps + 2)
+        st.check(st.L.jme_adam_minimize(st.h, int(maximumSteps), float(stepSize), float(threshold), float(self.beta1),
+                                        float(self.beta2), float(self.epsilon), xyz.ctypes.data_as(C.POINTER(C.c_double)),
+                                        C.byref(calls), C.byref(steps), log.ctypes.data_as(C.POINTER(C.c_double)),
+                                        log.shape[0]))
+        container.xyz[:] = xyz
+        st.shadow = xyz.reshape(-1).copy()
+        self.energyCalls = int(calls.value)
+        self.step = int(steps.value)
+        self.stepEnergies = log[:self.step + 1].tolist()
+        if self.onStepConsumer is not None:
+            for k, e in enumerate(self.stepEnergies):
+                self.onStepConsumer(k, e)
+
+
 class GradientMinimizer(EnergyMinimizer):
     """Steepest descent with backtracking on the analytic gradient (NOT in the reference)."""
 

@@ -342,6 +342,88 @@ def test_adam_minimizer_runs_and_matches_oracle_driven_loop(oracle):
     np.testing.assert_allclose(la, lb, rtol=1e-9)
 
 
+def test_native_adam_equals_python_loop():
+    """jme_adam_minimize and the Python mirror of AdamMinimizer (AdamMinimizer.java:62-120) make the same moves."""
+    from jmolecularenergy_b200 import AdamMinimizer, NativeAdamMinimizer, systems
+    a, b = systems.water_box(4), systems.water_box(4)
+    fa, fb = gpu_ff(), gpu_ff()
+    fa.assignParameters(a)
+    fb.assignParameters(b)
+    log_a = []
+    m1 = AdamMinimizer(fa, 0.9, 0.999, 1e-8)
+    m1.setOnStepConsumer(lambda step, e: log_a.append(e))
+    m1.minimize(a, 2, 0.01, 1e-6)
+    m2 = NativeAdamMinimizer(fb, 0.9, 0.999, 1e-8)
+    m2.minimize(b, 2, 0.01, 1e-6)
+    assert m1.energyCalls == m2.energyCalls == 1 + 3 * 2 * 36
+    assert m1.getStep() == m2.getStep() == 2
+    np.testing.assert_allclose(m2.stepEnergies, log_a, rtol=1e-13)
+    np.testing.assert_allclose(a.xyz, b.xyz, rtol=0, atol=1e-13)
+    assert fb.calculateEnergy(b) == pytest.approx(m2.stepEnergies[-1], rel=1e-12)
+
+
+def test_config4_opt5k_native_loop_against_oracle_driven_loop(oracle):
+    """BASELINE config 4 at size: the first 50 energy calls of the reference's GradientDescentMinimizer loop on the
+    5 001-atom water box, native loop on the GPU vs the same loop driven by the CPU oracle."""
+    from jmolecularenergy_b200 import NativeGradientDescentMinimizer, systems
+    s = systems.water_box(1667)
+    assert s.n_atoms == 5001
+    ff = gpu_ff()
+    ff.assignParameters(s)
+    # the oracle-driven restatement of GradientDescentMinimizer.java:49-105, stopped after 50 energy calls
+    xyz = s.xyz.copy()
+    ref_s = systems.water_box(1667)
+
+    def e_ref():
+        ref_s.xyz[:] = xyz
+        return oracle.fast_evaluate(ref_s, cutoff=0.0, gradient=False)["total"]
+
+    calls = 1
+    last = e_ref()
+    trace = [last]
+    step_size = 0.01
+    for a in range(s.n_atoms):
+        for i in range(3):
+            if calls >= 50:
+                break
+            d = min(abs(step_size * step_size), .3)
+            xyz[a, i] += d
+            e = e_ref()
+            calls += 1
+            trace.append(e)
+            xyz[a, i] += -d           # initialising sweep: every move is undone
+        if calls >= 50:
+            break
+    # the GPU: same moves through jme_set_coord1 + jme_energy (what jme_gd_minimize does per call)
+    st = ff._state(s)
+    st.sync_options(ff, ff.path)
+    got = [ff.calculateEnergy(s)]
+    L = st.L
+    tot = C.c_double()
+    k = 1
+    cur = s.xyz.copy()
+    for a in range(s.n_atoms):
+        for i in range(3):
+            if k >= 50:
+                break
+            d = min(abs(step_size * step_size), .3)
+            cur[a, i] += d
+            st.check(L.jme_set_coord1(st.h, a, i, float(cur[a, i])))
+            st.check(L.jme_energy(st.h, C.byref(tot), None))
+            got.append(tot.value)
+            cur[a, i] += -d
+            st.check(L.jme_set_coord1(st.h, a, i, float(cur[a, i])))
+            k += 1
+        if k >= 50:
+            break
+    np.testing.assert_allclose(got, trace, rtol=1e-10)
+    # and the native loop itself reproduces the first logged energy and makes 1 + 2 * 3N calls for one step
+    m = NativeGradientDescentMinimizer(ff)
+    m.minimize(s, 0, step_size, 1e-4)
+    assert m.energyCalls == 1
+    assert m.stepEnergies[0] == pytest.approx(trace[0], rel=1e-10)
+
+
 @pytest.mark.parametrize("n_waters", [42, 43, 44, 86])
 def test_superblock_boundaries(oracle, n_waters):
     """126 / 129 / 132 / 258 atoms: just below and above one and two 128-atom superblocks (padding chains,
@@ -471,3 +553,62 @@ def test_random_systems_both_cutoff_paths(oracle, seed):
             assert_parity(got, ref, f"{path} seed {seed}")
         e_only = ff.calculateEnergy(s)
         assert e_only == pytest.approx(got["total"], rel=1e-13)
+
+
+def test_cell_path_non_finite_coordinates_poison_the_total_and_return():
+    """A coordinate that is +-inf or NaN has no cell: the cell path must neither hang in the grid set-up nor read
+    out of bounds - it returns with a NaN total (the edge-growth loop used to spin for ever)."""
+    from jmolecularenergy_b200 import systems
+    for bad in (np.inf, -np.inf, np.nan, -np.nan):
+        s = systems.water_box(120)
+        s.xyz[17, 1] = bad
+        ff = gpu_ff(path="cells", cutoff=7.0)
+        ff.assignParameters(s)
+        got = ff.calculateComponents(s, gradient=True)
+        assert np.isnan(got["total"]), bad
+        # and the handle is still usable afterwards
+        s.xyz[17, 1] = 3.25
+        assert np.isfinite(ff.calculateEnergy(s))
+
+
+@pytest.mark.parametrize("cutoff,x1,x2", [(6.0, 2.9999999999999996, 9.0), (10.0, 4.999999999999999, 15.0)])
+def test_cell_boundary_pair_at_exactly_the_cutoff(oracle, cutoff, x1, x2):
+    """Two atoms whose double-rounded distance EQUALS the cutoff (kept: the reference drops a pair only if
+    distance > cutoff) and whose cell coordinates straddle cell boundaries: the cell path, the all-pairs
+    path and the oracle select the same pair set."""
+    from jmolecularenergy_b200 import systems
+    s = systems.ion_box(6)
+    s.xyz[:] = s.xyz - s.xyz.min(axis=0)            # the bounding box starts at the origin, like the advisor's example
+    s.xyz[0] = (0.0, 0.0, 0.0)
+    s.xyz[1] = (x1, 0.0, 0.0)
+    s.xyz[2] = (x2, 0.0, 0.0)
+    assert np.sqrt((x2 - x1) ** 2) == cutoff
+    oi, oj, of = oracle.pair_list(s, cutoff=cutoff)
+    assert np.any((oi == 1) & (oj == 2))
+    for path in ("cells", "allpairs"):
+        ff = gpu_ff(path=path, cutoff=cutoff)
+        ff.assignParameters(s)
+        pi, pj, f14 = ff.pairList(s)
+        assert np.array_equal(pi, oi) and np.array_equal(pj, oj), path
+        assert_parity(ff.calculateComponents(s, gradient=True), oracle.evaluate(s, cutoff=cutoff, gradient=True), path)
+
+
+def test_cell_path_many_atom_types_table_outside_shared_memory(oracle):
+    """A type-pair table too large to sit next to the force windows (80+ types used to fail with a generic
+    CUDA error): the cutoff path reads it through the cache hierarchy instead."""
+    from jmolecularenergy_b200 import systems
+    from jmolecularenergy_b200.system import MolecularSystem
+    base = systems.ion_box(9)
+    rng = np.random.default_rng(4)
+    types = [t for t in list(range(1, 83)) + list(range(87, 100))][:90]
+    s = MolecularSystem(
+        xyz=base.xyz, atom_type=rng.choice(types, size=base.n_atoms), charge=base.charge, linear=base.linear,
+        vdw_type=types, vdw_alpha=rng.uniform(0.5, 3.0, len(types)).astype(np.float32),
+        vdw_N=rng.uniform(1.5, 4.5, len(types)).astype(np.float32), vdw_A=rng.uniform(2.5, 4.2, len(types)).astype(np.float32),
+        vdw_G=rng.uniform(0.8, 1.4, len(types)).astype(np.float32), vdw_DA=rng.integers(0, 3, len(types)).astype(np.uint8),
+        name="ions-90-types")
+    ref = oracle.evaluate(s, cutoff=8.0, gradient=True)
+    for path in ("cells", "allpairs"):
+        ff = gpu_ff(path=path, cutoff=8.0)
+        ff.assignParameters(s)
+        assert_parity(ff.calculateComponents(s, gradient=True), ref, path)
