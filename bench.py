@@ -327,6 +327,35 @@ def main():
     res = unpack((out if world == 1 else out_full).cpu().numpy(), n, False)
     pairs = res["pairs"]
 
+    # ---- N > 1: the sharded result against an unsharded evaluation of the same system on this rank's GPU
+    #      (energies and pair count on every rank, the gradient rows each rank owns)
+    parity = None
+    if world > 1:
+        ev1 = ShardedMMFF94(system, cutoff=cfg["cutoff"], path=cfg["path"], rank=0, world=1)
+        out1 = ev1.new_output(True)
+        ev1.set_coords(xyz_dev)
+        ev1.evaluate_into(out1, True)
+        torch.cuda.synchronize()
+        ref1 = out1.cpu().numpy()
+        got_head = out_full[:10].cpu().numpy()
+        e_err = float(np.max(np.abs(got_head[:8] - ref1[:8]) / np.maximum(np.abs(ref1[:8]), 1e-3)))
+        g_ref = ref1[10:10 + 3 * n].reshape(n, 3)[a0:a1]
+        g_got = grad_own.cpu().numpy()[:3 * (a1 - a0)].reshape(-1, 3)
+        floor = 1e-10 * max(1.0, float(np.abs(ref1[10:]).max()))
+        g_err = float(np.max(np.abs(g_got - g_ref) / (np.abs(g_ref) + floor / 1e-8))) if a1 > a0 else 0.0
+        ok = e_err <= 1e-10 and g_err <= 1e-8 and int(round(got_head[8])) == int(round(ref1[8]))
+        t = torch.tensor([e_err, g_err, 0.0 if ok else 1.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        parity = {"parity_checked": True, "ok": bool(t[2].item() == 0.0), "energy_rel_err_max": float(t[0].item()),
+                  "gradient_rel_err_max": float(t[1].item()), "pairs_equal": int(round(got_head[8])) == int(round(ref1[8])),
+                  "against": "an unsharded (world = 1) evaluation of the same coordinates on every rank's GPU; tolerances 1e-10 "
+                             "(energies) and 1e-8 relative with a 1e-10 x max floor (owned gradient rows)"}
+        ev1.close()
+        del out1
+        torch.cuda.empty_cache()
+        if not parity["ok"]:
+            raise SystemExit(f"sharded evaluation differs from the unsharded one: {parity}")
+
     # ---- timed region: K steps, each bracketed by CUDA events on the launching stream, L2 flushed between
     sampler = ClockSampler(local_rank)
     launches0 = ev.launch_count()
@@ -446,6 +475,9 @@ def main():
             "wall_s_timed_region": t_wall,
             "energy_kcal_mol": res["total"],
         }
+        if parity is not None:
+            line["parity"] = parity
+            line["parity_checked"] = True
         if not args.no_cpu_baseline:
             base, _, _ = cpu_baseline(args.workload, faithful=False)
             line["cpu_baseline"] = base

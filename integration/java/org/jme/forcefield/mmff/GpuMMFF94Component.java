@@ -1,0 +1,136 @@
+/*
+ * GpuMMFF94Component - the drop-in: one EnergyComponent that returns the whole MMFF94 energy from libjme_b200.so,
+ * installed in place of the seven CPU components of MMFF94.java:98 through the reference's own registry
+ * (ForceField.addEnergyComponent / removeEnergyComponent, ForceField.java:85-109).  Panama FFM, JDK 22+.
+ * Not compiled in the repository's image (no JDK there); the struct marshalling is in JmeSystemLayout.java.
+ */
+package org.jme.forcefield.mmff;
+
+import static java.lang.foreign.ValueLayout.ADDRESS;
+import static java.lang.foreign.ValueLayout.JAVA_DOUBLE;
+import static java.lang.foreign.ValueLayout.JAVA_INT;
+import static java.lang.foreign.ValueLayout.JAVA_LONG;
+
+import java.lang.foreign.Arena;
+import java.lang.foreign.FunctionDescriptor;
+import java.lang.foreign.Linker;
+import java.lang.foreign.MemorySegment;
+import java.lang.foreign.SymbolLookup;
+import java.lang.invoke.MethodHandle;
+import java.util.ArrayList;
+import java.util.Objects;
+import org.jme.forcefield.EnergyComponent;
+import org.openscience.cdk.interfaces.IAtom;
+import org.openscience.cdk.interfaces.IAtomContainer;
+
+public final class GpuMMFF94Component extends EnergyComponent implements AutoCloseable {
+
+    private static final Linker LINKER = Linker.nativeLinker();
+    private static final SymbolLookup LIB = SymbolLookup.libraryLookup(System.getProperty("jme.b200.lib", "libjme_b200.so"), Arena.global());
+
+    private static MethodHandle h(String name, FunctionDescriptor fd) {
+        return LINKER.downcallHandle(LIB.find(name).orElseThrow(() -> new UnsatisfiedLinkError(name)), fd);
+    }
+
+    private static final MethodHandle CREATE = h("jme_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle DESTROY = h("jme_destroy", FunctionDescriptor.ofVoid(ADDRESS));
+    private static final MethodHandle OPTIONS = h("jme_set_options", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_DOUBLE, JAVA_DOUBLE, JAVA_INT));
+    private static final MethodHandle COORDS = h("jme_set_coords", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG));
+    private static final MethodHandle COORD1 = h("jme_set_coord1", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, JAVA_INT, JAVA_DOUBLE));
+    private static final MethodHandle ENERGY = h("jme_energy", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle GRADIENT = h("jme_energy_gradient", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle LASTERR = h("jme_last_error", FunctionDescriptor.of(ADDRESS, ADDRESS));
+    private static final MethodHandle CREATEERR = h("jme_last_create_error", FunctionDescriptor.of(ADDRESS));
+
+    private Arena arena = Arena.ofShared();
+    private MemorySegment handle = MemorySegment.NULL;
+    private IAtomContainer bound;          // container the handle was created for
+    private Object boundPairMap;           // identity of "mmff.nonBondedInteraction": a new map on every assignParameters
+    private double[] shadow;               // coordinates last uploaded (to find the single moved coordinate)
+    private MemorySegment xyz, total, comps;
+
+    /** Install on an MMFF94 instance: the seven CPU components out, this one in. */
+    public static GpuMMFF94Component install(MMFF94 ff) {
+        for (EnergyComponent c : new ArrayList<>(ff.getEnergyComponents())) ff.removeEnergyComponent(c);
+        GpuMMFF94Component gpu = new GpuMMFF94Component();
+        ff.addEnergyComponent(gpu);          // calls setForceField(ff) for us (ForceField.java:96)
+        return gpu;
+    }
+
+    @Override
+    public double calculateEnergy(IAtomContainer mol) {
+        Objects.requireNonNull(forceField);
+        if (mol.isEmpty()) return 0;
+        MMFF94.checkParametersAssigned(mol.getAtom(0));                       // same exception as MMFF94.java:371-375
+        Object pairMap = mol.getProperty(MMFF94.MMFF94_NON_BONDED_INTERACTION);
+        if (mol != bound || pairMap != boundPairMap) marshal(mol, pairMap);   // (re)assignParameters happened
+        check((int) invoke(OPTIONS, handle, forceField.getCutoffDistance(), forceField.getDielectricConstant(),
+                forceField.getEnergyUnit().ordinal()));                       // KCAL, KJ, JOULE = 0, 1, 2
+        uploadCoordinates(mol);
+        check((int) invoke(ENERGY, handle, total, comps));
+        return total.get(JAVA_DOUBLE, 0);
+    }
+
+    /** Addition (the reference has no gradient): dE/dx, [n][3], in the force field's energy unit per Angstrom. */
+    public double[] calculateGradient(IAtomContainer mol) {
+        calculateEnergy(mol);                                                 // binds, uploads
+        try (Arena tmp = Arena.ofConfined()) {
+            MemorySegment g = tmp.allocate(JAVA_DOUBLE, 3L * mol.getAtomCount());
+            check((int) invoke(GRADIENT, handle, total, comps, g));
+            return g.toArray(JAVA_DOUBLE);
+        }
+    }
+
+    private void uploadCoordinates(IAtomContainer mol) {
+        int n = mol.getAtomCount(), changed = 0, last = -1;
+        double[] now = new double[3 * n];
+        for (IAtom a : mol.atoms()) {
+            javax.vecmath.Point3d p = a.getPoint3d();
+            int i = 3 * a.getIndex();
+            now[i] = p.x; now[i + 1] = p.y; now[i + 2] = p.z;
+        }
+        if (shadow != null) for (int k = 0; k < 3 * n; k++) if (now[k] != shadow[k]) { changed++; last = k; }
+        if (shadow != null && changed == 0) return;
+        if (shadow != null && changed == 1) {                                 // minimizer fast path: 8 bytes, not 24 n
+            check((int) invoke(COORD1, handle, (long) (last / 3), last % 3, now[last]));
+        } else {
+            MemorySegment.copy(now, 0, xyz, JAVA_DOUBLE, 0, 3 * n);
+            check((int) invoke(COORDS, handle, xyz, (long) n));
+        }
+        shadow = now;
+    }
+
+    /** Flatten what assignParameters left on the container (JmeSystemLayout.write) and create the device handle. */
+    private void marshal(IAtomContainer mol, Object pairMap) {
+        close0();
+        arena.close();
+        arena = Arena.ofShared();
+        int n = mol.getAtomCount();
+        try (Arena tmp = Arena.ofConfined()) {                                // jme_create copies everything it is given
+            MemorySegment sys = JmeSystemLayout.write(tmp, mol);
+            MemorySegment out = tmp.allocate(ADDRESS);
+            int rc = (int) invoke(CREATE, sys, out);
+            if (rc != 0) throw new RuntimeException(((MemorySegment) invoke(CREATEERR)).reinterpret(4096).getString(0));
+            handle = out.get(ADDRESS, 0);
+        }
+        xyz = arena.allocate(JAVA_DOUBLE, 3L * n);
+        total = arena.allocate(JAVA_DOUBLE);
+        comps = arena.allocate(JAVA_DOUBLE, 7);
+        bound = mol; boundPairMap = pairMap; shadow = null;
+    }
+
+    private void check(int rc) {
+        if (rc != 0) throw new RuntimeException(((MemorySegment) invoke(LASTERR, handle)).reinterpret(4096).getString(0));
+    }
+
+    private static Object invoke(MethodHandle m, Object... a) {
+        try { return m.invokeWithArguments(a); } catch (Throwable t) { throw new RuntimeException(t); }
+    }
+
+    private void close0() {
+        if (!handle.equals(MemorySegment.NULL)) { invoke(DESTROY, handle); handle = MemorySegment.NULL; }
+    }
+
+    @Override
+    public void close() { close0(); arena.close(); }
+}

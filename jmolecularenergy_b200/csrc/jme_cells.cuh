@@ -58,6 +58,21 @@ struct GridParams {
     int n_seg;               // ny * nz * nsx
 };
 
+// Cells whose atoms a shard of the cluster path touches: the cells of its segments plus the cells its force windows
+// reach forward (reach cell layers + reach cell rows + the rest of the last row).  Everything before and after
+// needs no sorted record on this rank.  world == 1 or the per-atom-list path (n_seg == 0): all cells.
+__device__ __forceinline__ void shard_cell_range(const GridParams& g, int rank, int world, int& c_lo, int& c_hi) {
+    c_lo = 0; c_hi = g.ncell;
+    if (world <= 1 || g.n_seg <= 0) return;
+    const long long s0 = (long long)g.n_seg * rank / world, s1 = (long long)g.n_seg * (rank + 1) / world;
+    auto first_cell = [&](long long s) { return s >= g.n_seg ? g.ncell : (int)(s / g.nsx) * g.nx + (int)(s % g.nsx) * g.seg_len; };
+    c_lo = first_cell(s0);
+    const long long last_row = (s1 + g.nsx - 1) / g.nsx;                       // one past the last row with a segment of the shard
+    const long long hi_row = last_row + (long long)g.reach * g.ny + g.reach;   // rows its windows can reach
+    c_hi = (int)(hi_row * g.nx < (long long)g.ncell ? hi_row * g.nx : (long long)g.ncell);
+    if (s1 <= s0) c_hi = c_lo;
+}
+
 struct alignas(32) PosQ { double x, y, z, q; };
 constexpr int kPadType = 0x80;          // stype of a padding record (cluster path): type 0, flag bit 7
 
@@ -77,8 +92,7 @@ struct CellArrays {
     int pad;                 // every cell is padded to a multiple of `pad` sorted positions (1: no padding)
     int n_spad;              // capacity of the arrays indexed by sorted position: n + (pad - 1) * min(n, max_cells)
     int seg_target;          // wanted number of segments (cluster path), 0 otherwise
-    int ring;                // cluster path: slots per neighbour row of the force windows
-    unsigned int ring_magic; // floor(2^32 / ring)
+    int ring;                // cluster path: slots of a warp's force window (shared by the rows, cl_layout_kernel)
     int* flags;              // [4] device flags: [0] list overflow, [1] non-finite coordinate, [2] window fallback used
     int* cell_of;            // [n] cell index per original atom
     int* count;              // [max_cells + 1]
@@ -98,6 +112,7 @@ struct CellArrays {
     long long n_excl_ent;
     double* bbox_part;       // [blocks][6]
     int bbox_blocks;
+    int rank, world;         // shard of the cluster path (only the cells it touches are sorted)
     int* work_ctr;           // [2] dynamic work distribution: next (cell, part) item / next atom group (or segment);
                              // work_ctr and flags are one 32-byte control block
 };
@@ -279,10 +294,14 @@ __global__ void __launch_bounds__(kScanBlock) scan_add_kernel(const GridParams* 
 
 // ---- 3. sort -----------------------------------------------------------------------------------
 __global__ void cell_scatter_kernel(int n, const int* __restrict__ cell_of, const int* __restrict__ start,
-                                    int* __restrict__ cursor, int* __restrict__ order_tmp) {
+                                    int* __restrict__ cursor, int* __restrict__ order_tmp, const GridParams* __restrict__ g,
+                                    int rank, int world) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n) return;
     const int c = cell_of[a];
+    int c_lo, c_hi;
+    shard_cell_range(*g, rank, world, c_lo, c_hi);
+    if (c < c_lo || c >= c_hi) return;
     order_tmp[start[c] + atomicAdd(&cursor[c], 1)] = a;
 }
 
@@ -293,6 +312,11 @@ __global__ void cell_rank_gather_kernel(DeviceSystem S, CellArrays C) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= S.n) return;
     const int c = C.cell_of[a];
+    {
+        int c_lo, c_hi;
+        shard_cell_range(*C.grid, C.rank, C.world, c_lo, c_hi);
+        if (c < c_lo || c >= c_hi) { C.sorted_of[a] = 0x7fffffff; return; }    // not sorted on this rank: matches nothing
+    }
     const int b = C.start[c], m = C.count[c];
     int rank = 0;
     for (int q = b; q < b + m; ++q) rank += C.order_tmp[q] < a;
@@ -848,6 +872,7 @@ struct CellPlan {
     double* d_gj_ovf = nullptr;
     int* d_excl_src = nullptr;
     uint2* d_cellmask = nullptr;   // [max_cells] which force slots were written for a cell (cl_cellmask_kernel)
+    unsigned int* d_layout = nullptr;   // [max_cells][16] window layout per segment (cl_layout_kernel)
     std::vector<void*> new_allocs;
 
     std::vector<void*> take_new_allocs() { std::vector<void*> v; v.swap(new_allocs); return v; }
@@ -943,7 +968,7 @@ inline int build_cell_plan(CellPlan& p, const HostSystem& hs, const DeviceSystem
             if (!cell_alloc(p, &p.d_clist, (size_t)std::max(1, n) * p.list_cap, err) || !cell_alloc(p, &p.d_count, std::max(1, n), err) ||
                 !cell_alloc(p, &p.d_gi, 3 * ns, err) || !cell_alloc(p, &p.d_gj, (size_t)2 * 13 * 3 * ns, err) ||
                 !cell_alloc(p, &p.d_gj_ovf, 3 * ns, err) || !cell_alloc(p, &p.d_excl_src, hs.excl_ent.size(), err) ||
-                !cell_alloc(p, &p.d_cellmask, (size_t)a.max_cells, err))
+                !cell_alloc(p, &p.d_cellmask, (size_t)a.max_cells, err) || !cell_alloc(p, &p.d_layout, (size_t)16 * a.max_cells, err))
                 return JME_ERR_NOMEM;
             cudaMemset(p.d_gj_ovf, 0, 3 * ns * sizeof(double));      // the reduction leaves it zero again after every use
             std::vector<int> src(hs.excl_ent.size());
@@ -962,6 +987,8 @@ inline int build_cell_plan(CellPlan& p, const HostSystem& hs, const DeviceSystem
     p.cutoff = cutoff;
     p.world = world;
     p.rank = rank;
+    p.arr.rank = cluster != 0 ? rank : 0;        // the per-atom-list path shards by atom index and sorts everything
+    p.arr.world = cluster != 0 ? world : 1;
     p.i_begin = (int)((long long)n * rank / world);
     p.i_end = (int)((long long)n * (rank + 1) / world);
     p.sorted_valid = false;
@@ -995,7 +1022,7 @@ inline int run_cell_sort(CellPlan& p, const DeviceSystem& ds, cudaStream_t st, u
     scan_local_kernel<<<scan_blocks, kScanBlock, 0, st>>>(a.grid, a.count, a.start, a.block_sums, a.pad);
     scan_sums_kernel<<<1, 1024, 0, st>>>(a.grid, a.block_sums);
     scan_add_kernel<<<scan_blocks, kScanBlock, 0, st>>>(a.grid, a.start, a.block_sums);
-    cell_scatter_kernel<<<nb, 256, 0, st>>>(n, a.cell_of, a.start, a.cursor, a.order_tmp);
+    cell_scatter_kernel<<<nb, 256, 0, st>>>(n, a.cell_of, a.start, a.cursor, a.order_tmp, a.grid, a.rank, a.world);
     cell_rank_gather_kernel<<<nb, 256, 0, st>>>(ds, a);
     launches += 9;
     if (a.n_excl_ent > 0) {

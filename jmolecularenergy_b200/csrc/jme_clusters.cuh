@@ -85,6 +85,48 @@ __device__ __forceinline__ int cl_ring_mod(int t, int ring, unsigned int magic) 
     return r >= ring ? r - ring : r;
 }
 
+// ---- force-window layout ------------------------------------------------------------------------------
+// The window of a sweeping warp is one pool of `pool` FP64 slots (x 3 planes) shared by the <= 13 rows of the half
+// shell.  Row o of segment s gets a ring of cap(s, o) slots = the largest number of atoms its (2 reach + 1)-cell
+// window ever holds while the segment is swept, so no partner ever falls outside its ring; only if the rows together
+// need more than the pool are the rings shortened in proportion (partners beyond a ring then go through atomics).
+// One warp per segment; layout[seg * 16 + o] = base | cap << 16.
+__global__ void __launch_bounds__(256)
+cl_layout_kernel(CellArrays A, int pool, unsigned int* __restrict__ layout) {
+    const GridParams& g = *A.grid;
+    const int lane = threadIdx.x & 31;
+    const int n_warps = gridDim.x * (blockDim.x >> 5);
+    for (int seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); seg < g.n_seg; seg += n_warps) {
+        const int row = seg / g.nsx, sx = seg % g.nsx;
+        const int xa = sx * g.seg_len, xb = min(xa + g.seg_len, g.nx);
+        const int cy = row % g.ny, cz = row / g.ny;
+        int need = 0;
+        if (lane < g.n_half) {
+            int dy, dz;
+            cl_row_offset(lane, g.reach, dy, dz);
+            const int y2 = cy + dy, z2 = cz + dz;
+            if (y2 >= 0 && y2 < g.ny && z2 < g.nz) {
+                const int rb = (z2 * g.ny + y2) * g.nx;
+                for (int x = xa; x < xb; ++x)
+                    need = max(need, A.start[rb + min(x + g.reach, g.nx - 1) + 1] - A.start[rb + max(x - g.reach, 0)]);
+            }
+        }
+        need = min(need, 0xffff);
+        int total = need;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+        int cap = need;
+        if (total > pool) cap = (int)((long long)need * pool / total);     // (a row that needs slots keeps at least ... 0: all atomics)
+        int incl = cap;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane < 16) layout[seg * 16 + lane] = (unsigned int)(incl - cap) | ((unsigned int)cap << 16);
+    }
+}
+
 // ---- cluster lists -----------------------------------------------------------------------------------
 struct ClListArgs {
     uint2* list;                   // [clusters][cap]
@@ -92,8 +134,7 @@ struct ClListArgs {
     int cap;
     int parts;                     // warps sharing one cell (small systems)
     int rank, world;
-    int ring;                      // window slots per neighbour row (the evaluation kernel's shared-memory budget)
-    unsigned int ring_magic;       // floor(2^32 / ring)
+    const unsigned int* layout;    // [segments][16] ring of every half-shell row in the sweeping warp's window (cl_layout_kernel)
 };
 
 // if (pred) base[index] = v (8 bytes), as a predicated streaming store with a single-instruction address
@@ -113,12 +154,14 @@ cl_list_kernel(CellArrays A, ClListArgs P) {
     __shared__ int s_jb[kListWarps][16];        // first candidate of half-shell row o
     __shared__ int s_cw[kListWarps][16];        // first position of row o's window for this cell
     __shared__ int s_p0[kListWarps][16];        // ring origin of row o: first position of its window for the SEGMENT
+    __shared__ int4 s_ring[kListWarps][16];     // ring of row o: {first slot, slots, floor(2^32 / slots), -}
     __shared__ int s_off[kListWarps][17];       // exclusive prefix of the candidate counts (virtual candidate index)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float2 (*fis)[4] = s_fi[warp];
     int* jbs = s_jb[warp];
     int* cws = s_cw[warp];
     int* p0s = s_p0[warp];
+    int4* rings = s_ring[warp];
     int* off = s_off[warp];
     const GridParams g = *A.grid;
     const unsigned int lt_mask = (1u << lane) - 1u;
@@ -142,6 +185,7 @@ cl_list_kernel(CellArrays A, ClListArgs P) {
         if (k0 >= k1) continue;
         const int cx = c % g.nx, cy = (c / g.nx) % g.ny, cz = c / (g.nx * g.ny);
         const int xa = cx / g.seg_len * g.seg_len;                   // first cell of the segment that sweeps this cell
+        const int seg = (cz * g.ny + cy) * g.nsx + cx / g.seg_len;
         const int a_begin = c0 + C * k0, a_end = c0 + C * k1;        // sorted positions of this item's clusters
         int total;
         {   // candidate range of half-shell row `lane` and the prefix sums that flatten the <= 13 ranges into one
@@ -169,7 +213,12 @@ cl_list_kernel(CellArrays A, ClListArgs P) {
             }
             total = __shfl_sync(0xffffffffu, incl, 31);
             __syncwarp();
-            if (lane < 16) { jbs[lane] = jb; cws[lane] = cw; p0s[lane] = p0; off[lane] = incl - len; }
+            if (lane < 16) {
+                jbs[lane] = jb; cws[lane] = cw; p0s[lane] = p0; off[lane] = incl - len;
+                const unsigned int lay = P.layout[seg * 16 + lane];
+                const int cap = (int)(lay >> 16);
+                rings[lane] = make_int4((int)(lay & 0xffffu), cap, cap > 0 ? (int)(0x100000000ull / (unsigned long long)cap) : 0, 0);
+            }
             if (lane == 16) off[16] = incl - len;                     // = total for lane >= H (len == 0)
         }
         for (int ch = a_begin; ch < a_end; ch += 32) {              // at most 32 atoms (32 / C clusters) at a time
@@ -205,9 +254,10 @@ cl_list_kernel(CellArrays A, ClListArgs P) {
                     jj[k] = j;
                     // the partner's slot in the force window of the sweeping warp: ring index counted from the ring
                     // origin of its row; a partner further from the window start than the ring is long is flagged
-                    const int slot = r[k] * P.ring + cl_ring_mod(valid ? j - p0s[r[k]] : 0, P.ring, P.ring_magic);
+                    const int4 rg = rings[r[k]];
+                    const int slot = rg.x + (rg.y > 0 ? cl_ring_mod(valid ? j - p0s[r[k]] : 0, rg.y, (unsigned int)rg.z) : 0);
                     meta[k] = (unsigned int)slot | ((unsigned int)__float_as_int(a.w) << kMetaTypeShift) |
-                              (j - cws[r[k]] >= P.ring ? kMetaOvf : 0u);
+                              (j - cws[r[k]] >= rg.y ? kMetaOvf : 0u);
                 }
                 unsigned long long px[kListK / 2], py[kListK / 2], pz[kListK / 2];
 #pragma unroll
@@ -308,8 +358,9 @@ struct ClPairArgs {
     const int* count;              // [clusters]
     int cap;
     int rank, world;
-    int ring;                      // window slots per neighbour row
-    int n_spad;                    // pitch of the per-position arrays below
+    int pool;                      // slots of a warp's force window (cl_layout_kernel shares them among the rows)
+    const unsigned int* layout;    // [segments][16]
+    int n_spad;                    // (capacity of the per-position arrays below)
     double* gi;                    // [position][3] i-side sums by sorted position
     double* gj;                    // [2 * kClMaxRows][cl_pitch][3] j-side window flushes: slot 2 * row + (segment & 1)
     double* gj_ovf;                // [position][3] atomically accumulated contributions of atoms beyond a window's capacity
@@ -365,11 +416,11 @@ cl_pair_kernel(DeviceSystem S, CellArrays A, ClPairArgs P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int TT = S.n_types * S.n_types;
-    const int RING = P.ring;
-    const int plane = (int)cl_window_plane(RING);                // doubles between the x, y and z planes
+    const int POOL = P.pool;
+    const int plane = (int)cl_window_plane(POOL);                // doubles between the x, y and z planes
     PairConst* s_table = reinterpret_cast<PairConst*>(smem_raw);
     unsigned char* wbase = smem_raw + (TSM ? (((size_t)TT * sizeof(PairConst) + 15) & ~(size_t)15) : 0) +
-                           (size_t)warp * cl_warp_smem(GRAD, RING);
+                           (size_t)warp * cl_warp_smem(GRAD, POOL);
     double* acc = reinterpret_cast<double*>(wbase);                                      // [3][plane] (GRAD)
     int* rowtab = reinterpret_cast<int*>(wbase + (GRAD ? 3 * (size_t)plane * sizeof(double) : 0));   // [cell of the segment][row]: window start
     int* s_cnt = rowtab + kClMaxSegLen * kClRowPitch;                                    // list length of the batch's clusters
@@ -387,7 +438,7 @@ cl_pair_kernel(DeviceSystem S, CellArrays A, ClPairArgs P) {
     const int H = g.n_half;
     const PosQ* __restrict__ spq = A.spq;
     const long long s0 = (long long)g.n_seg * P.rank / P.world, s1 = (long long)g.n_seg * (P.rank + 1) / P.world;
-    const unsigned int dummy_meta = (unsigned int)(kClMaxRows * RING) | F::kAllExcl;    // lanes beyond the end of a list
+    const unsigned int dummy_meta = (unsigned int)POOL | F::kAllExcl;        // lanes beyond the end of a list: slot POOL
     const size_t np = cl_pitch(A.start[g.ncell]);                // positions per slot array (xyz interleaved)
 
     for (;;) {
@@ -406,7 +457,14 @@ cl_pair_kernel(DeviceSystem S, CellArrays A, ClPairArgs P) {
         if (q0 < q1) {
             // lane o < H looks after half-shell row o: its cell row, the ring origin (sorted position of ring slot 0)
             // and the flush frontier (first position not yet written to the slot array)
-            int my_rowbase = -1, my_p0 = 0, my_lo = 0;
+            int my_rowbase = -1, my_p0 = 0, my_lo = 0, my_base = 0, my_cap = 0;
+            unsigned int my_magic = 0;
+            if (lane < 16) {
+                const unsigned int lay = P.layout[seg * 16 + lane];
+                my_base = (int)(lay & 0xffffu);
+                my_cap = (int)(lay >> 16);
+                my_magic = my_cap > 0 ? (unsigned int)(0x100000000ull / (unsigned long long)my_cap) : 0u;
+            }
             if (lane < H) {
                 int dy, dz;
                 cl_row_offset(lane, g.reach, dy, dz);
@@ -431,14 +489,16 @@ cl_pair_kernel(DeviceSystem S, CellArrays A, ClPairArgs P) {
                     const int lo = __shfl_sync(FULL, my_lo, o);
                     const int hi = __shfl_sync(FULL, target, o);
                     const int p0 = __shfl_sync(FULL, my_p0, o);
+                    const int base = __shfl_sync(FULL, my_base, o), cap = __shfl_sync(FULL, my_cap, o);
+                    const unsigned int magic = __shfl_sync(FULL, my_magic, o);
                     if (rb < 0 || hi <= lo) continue;
                     double* dst = P.gj + ((size_t)(2 * o + slot_par) * np + lo) * 3;
-                    const int r0 = cl_ring_mod(lo - p0, RING, A.ring_magic);
+                    const int r0 = cap > 0 ? cl_ring_mod(lo - p0, cap, magic) : 0;
                     for (int d = lane; d < hi - lo; d += 32) {
-                        const bool in_ring = d < RING;                // positions beyond the capacity were never accumulated here
+                        const bool in_ring = d < cap;                 // positions beyond the ring were never accumulated here
                         int ri = r0 + d;
-                        if (ri >= RING) ri -= RING;
-                        const int idx = o * RING + ri;
+                        if (ri >= cap) ri -= cap;
+                        const int idx = base + ri;
                         double vx = 0, vy = 0, vz = 0;
                         if (in_ring) {
                             vx = acc[idx]; vy = acc[plane + idx]; vz = acc[2 * plane + idx];
@@ -519,14 +579,14 @@ cl_pair_kernel(DeviceSystem S, CellArrays A, ClPairArgs P) {
                     trow[a] = 0;
                 }
                 uint2 E0[K], E1[K];
-                PosQ GA[K], GB[K];
+                PosQ G[K], Gn[K];
                 load_entries(0, 0, E0);
                 if (il1 < nq) load_entries(il1, t1, E1);
 #pragma unroll
-                for (int k = 0; k < K; ++k) GA[k] = load_posq(spq + E0[k].x);
+                for (int k = 0; k < K; ++k) { G[k] = load_posq(spq + E0[k].x); Gn[k] = G[k]; }
 
                 // one trip: E0 / G are this trip's entries and records, E1 the next trip's entries (its records go to Gn)
-                auto trip = [&](const PosQ (&G)[K], PosQ (&Gn)[K]) -> bool {
+                do {
                     if (nxt_pending) {                        // the atoms fetched during the previous trip go to their parking place
                         __syncwarp();
                         park_cluster(nxt);
@@ -655,7 +715,7 @@ cl_pair_kernel(DeviceSystem S, CellArrays A, ClPairArgs P) {
                                         atomicAdd(P.gj_ovf + 3 * (size_t)E0[k].x + 1, gjy);
                                         atomicAdd(P.gj_ovf + 3 * (size_t)E0[k].x + 2, gjz);
                                         A.flags[2] = 1;
-                                        ri = kClMaxRows * RING;                   // and nothing to the window
+                                        ri = POOL;                                // and nothing to the window
                                         gjx = gjy = gjz = 0.0;
                                     }
                                 }
@@ -665,7 +725,7 @@ cl_pair_kernel(DeviceSystem S, CellArrays A, ClPairArgs P) {
                             }
                         }
                     }
-                    __syncwarp();                                 // window updates of this trip before those of the next
+                    // (the window updates of consecutive trips stay in program order: one warp, in-order shared-memory pipe)
                     if (t + 1 == T && GRAD && !EMIT) {            // the cluster is complete: reduce its i-side sums over the warp
                         constexpr int NV = C == 2 ? 8 : 16;
                         double v[NV];
@@ -683,13 +743,8 @@ cl_pair_kernel(DeviceSystem S, CellArrays A, ClPairArgs P) {
                     il1 = il2; t1 = t2; T1 = T2;
                     advance(il2, t2, T2);
 #pragma unroll
-                    for (int k = 0; k < K; ++k) { E0[k] = E1[k]; E1[k] = E2[k]; }
-                    return il < nq;
-                };
-                while (true) {
-                    if (!trip(GA, GB)) break;
-                    if (!trip(GB, GA)) break;
-                }
+                    for (int k = 0; k < K; ++k) { E0[k] = E1[k]; E1[k] = E2[k]; G[k] = Gn[k]; }
+                } while (il < nq);
                 (void)ci;
             }
             {   // the segment is done: everything still in the windows goes out
@@ -777,7 +832,12 @@ cl_reduce_kernel(CellArrays A, ClReduceArgs Q) {
     const bool use_ovf = A.flags[2] != 0;
     const int n_sorted = A.start[g.ncell];
     const size_t np = cl_pitch(n_sorted);
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_sorted; p += (gridDim.x - 1) * blockDim.x) {
+    // a shard only holds (and only wrote forces for) the positions of the cells it touches; the caller zeroed the rest
+    int c_lo, c_hi;
+    shard_cell_range(g, Q.rank, Q.world, c_lo, c_hi);
+    const int p_lo = A.start[c_lo], p_hi = A.start[c_hi];
+    const bool with_bonded = Q.world == 1;                        // sharded: bonded slots are added by cl_bonded_add_kernel
+    for (int p = p_lo + blockIdx.x * blockDim.x + threadIdx.x; p < p_hi; p += (gridDim.x - 1) * blockDim.x) {
         const int a = A.orig[p];
         if (a < 0) continue;                                      // padding
         const uint2 m = Q.cellmask[A.scell[p]];
@@ -803,12 +863,14 @@ cl_reduce_kernel(CellArrays A, ClReduceArgs Q) {
             gx += ov[0]; gy += ov[1]; gz += ov[2];
             ov[0] = 0.0; ov[1] = 0.0; ov[2] = 0.0;
         }
-        for (long long e = R.slot_ptr[a]; e < R.slot_ptr[a + 1]; ++e) {
-            const long long sl = R.slot_idx[e];
-            if (sl >= R.slot_lo && sl < R.slot_hi) {
-                gx += R.slots[3 * sl];
-                gy += R.slots[3 * sl + 1];
-                gz += R.slots[3 * sl + 2];
+        if (with_bonded) {
+            for (long long e = R.slot_ptr[a]; e < R.slot_ptr[a + 1]; ++e) {
+                const long long sl = R.slot_idx[e];
+                if (sl >= R.slot_lo && sl < R.slot_hi) {
+                    gx += R.slots[3 * sl];
+                    gy += R.slots[3 * sl + 1];
+                    gz += R.slots[3 * sl + 2];
+                }
             }
         }
         double* o = R.out + kOutHeader + 3 * (size_t)a;
@@ -816,6 +878,30 @@ cl_reduce_kernel(CellArrays A, ClReduceArgs Q) {
         o[1] = convert_unit(gy, R.unit_num, R.unit_den);
         o[2] = convert_unit(gz, R.unit_num, R.unit_den);
     }
+}
+
+// sharded evaluation: the bonded terms are split by term index, not by space - their gradient slots are added to the
+// (zeroed, then partly written) output by original atom index
+__global__ void __launch_bounds__(256)
+cl_bonded_add_kernel(ReduceArgs R) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= R.n) return;
+    double gx = 0, gy = 0, gz = 0;
+    bool any = false;
+    for (long long e = R.slot_ptr[a]; e < R.slot_ptr[a + 1]; ++e) {
+        const long long sl = R.slot_idx[e];
+        if (sl >= R.slot_lo && sl < R.slot_hi) {
+            gx += R.slots[3 * sl];
+            gy += R.slots[3 * sl + 1];
+            gz += R.slots[3 * sl + 2];
+            any = true;
+        }
+    }
+    if (!any) return;
+    double* o = R.out + kOutHeader + 3 * (size_t)a;
+    o[0] += convert_unit(gx, R.unit_num, R.unit_den);
+    o[1] += convert_unit(gy, R.unit_num, R.unit_den);
+    o[2] += convert_unit(gz, R.unit_num, R.unit_den);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
@@ -828,16 +914,15 @@ inline int cl_configure(CellPlan& p, const DeviceSystem& ds, std::string& err) {
     const size_t table = (((size_t)ds.n_types * ds.n_types * sizeof(PairConst)) + 15) & ~(size_t)15;
     p.cl_table_in_smem = table <= 48 * 1024 ? 1 : 0;
     const size_t tb = p.cl_table_in_smem ? table : 0;
-    // the ring length of the force windows from what kClWarps warps leave of the shared memory
+    // the slot pool of a warp's force window from what kClWarps warps leave of the shared memory
     const long long per_warp = ((long long)max_smem - (long long)tb) / kClWarps;
-    long long ring = (per_warp - (long long)cl_warp_smem(true, 0)) / (3 * kClMaxRows * (long long)sizeof(double));
-    ring = std::min<long long>(kClMaxRing, ring / 8 * 8);
-    if (ring < 32) { err = "cell path: not enough shared memory for the force windows"; return JME_ERR_UNSUPPORTED; }
-    p.arr.ring = (int)ring;
-    p.arr.ring_magic = (unsigned int)(0x100000000ull / (unsigned long long)ring);
+    long long pool = (per_warp - (long long)cl_warp_smem(true, 0)) / (3 * (long long)sizeof(double));
+    pool = std::min<long long>((1 << kMetaSlotBits) - 1, pool / 8 * 8);
+    if (pool < 256) { err = "cell path: not enough shared memory for the force windows"; return JME_ERR_UNSUPPORTED; }
+    p.arr.ring = (int)pool;
     p.cl_warps = kClWarps;
-    p.cl_smem_grad = tb + kClWarps * cl_warp_smem(true, (int)ring);
-    p.cl_smem_energy = tb + kClWarps * cl_warp_smem(false, (int)ring);
+    p.cl_smem_grad = tb + kClWarps * cl_warp_smem(true, (int)pool);
+    p.cl_smem_energy = tb + kClWarps * cl_warp_smem(false, (int)pool);
     // about four segments per resident warp
     p.arr.seg_target = 4 * p.sms * kClWarps;
     return JME_OK;
@@ -847,11 +932,13 @@ template <int C>
 inline int cl_run_lists_t(CellPlan& p, const DeviceSystem& ds, cudaStream_t st, uint64_t& launches, std::string& err) {
     ClListArgs A{};
     A.list = p.d_clist; A.count = p.d_count; A.cap = p.list_cap; A.rank = p.rank; A.world = p.world;
-    A.ring = p.arr.ring; A.ring_magic = p.arr.ring_magic;
+    A.layout = p.d_layout;
     const int grid = p.sms * kClListMinBlocks;
     const long long resident = (long long)grid * kListWarps;
     A.parts = (int)std::max(1ll, std::min(8ll, 2 * resident * 12 / std::max(1, ds.n)));
     cudaMemsetAsync(p.arr.work_ctr, 0, 2 * sizeof(int), st);
+    cl_layout_kernel<<<std::max(1, std::min(4 * p.sms, (ds.n + 2047) / 2048)), 256, 0, st>>>(p.arr, p.arr.ring, p.d_layout);
+    ++launches;
     cl_list_kernel<C><<<grid, kListThreads, 0, st>>>(p.arr, A);
     ++launches;
     if (p.arr.n_excl_ent > 0) {
@@ -870,7 +957,7 @@ inline int cl_run_lists(CellPlan& p, const DeviceSystem& ds, cudaStream_t st, ui
 
 inline void cl_fill_pair_args(CellPlan& p, ClPairArgs& P) {
     P.list = p.d_clist; P.count = p.d_count; P.cap = p.list_cap;
-    P.rank = p.rank; P.world = p.world; P.n_spad = p.n_spad + 1; P.ring = p.arr.ring;
+    P.rank = p.rank; P.world = p.world; P.n_spad = p.n_spad + 1; P.pool = p.arr.ring; P.layout = p.d_layout;
     P.gi = p.d_gi; P.gj = p.d_gj; P.gj_ovf = p.d_gj_ovf;
     P.epart = p.d_epart; P.cpart = p.d_cpart;
 }
@@ -912,6 +999,8 @@ inline int cl_run_reduce(CellPlan& p, const DeviceSystem& ds, const ReduceArgs& 
     Q.gi = p.d_gi; Q.gj = p.d_gj; Q.gj_ovf = p.d_gj_ovf; Q.cellmask = p.d_cellmask;
     Q.R = R;
     const int nt = kReduceWarps * 32;
+    if (R.want_grad && p.world > 1)          // a shard writes the atoms it touched only
+        cudaMemsetAsync(R.out + kOutHeader, 0, 3 * (size_t)ds.n * sizeof(double), st);
     if (R.want_grad) {
         cl_cellmask_kernel<<<std::max(1, std::min(4 * p.sms, (ds.n + 255) / 256)), 256, 0, st>>>(p.arr, p.rank, p.world, p.d_cellmask);
         ++launches;
@@ -920,8 +1009,11 @@ inline int cl_run_reduce(CellPlan& p, const DeviceSystem& ds, const ReduceArgs& 
     const int grid = (R.want_grad ? std::max(1, std::min(16 * p.sms, (ds.n + nt - 1) / nt)) : 0) + 1;
     cl_reduce_kernel<<<grid, nt, 0, st>>>(p.arr, Q);
     ++launches;
+    if (R.want_grad && p.world > 1 && R.slot_hi > R.slot_lo) {
+        cl_bonded_add_kernel<<<(ds.n + 255) / 256, 256, 0, st>>>(R);
+        ++launches;
+    }
     JME_CELL_CHECK();
-    (void)ds;
     return JME_OK;
 }
 
