@@ -395,6 +395,33 @@ def main():
     nb_ms = float(np.mean(nb[:got.value])) if got.value else float("nan")
     build_ms = float(np.mean(bl[:got.value])) if got.value else float("nan")
 
+    # ---- N > 1: where a step goes - CUDA events around the phases of an owner-mode step, max over ranks per phase
+    phases = None
+    if world > 1:
+        names = ["all_gather_coordinates", "local_evaluation", "all_reduce_energies", "reduce_scatter_gradient"]
+        acc = [0.0] * 4
+        n_ph = min(args.steps, 30)
+        for k in range(n_ph):
+            flush.fill_(k & 0xff)
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            e[0].record()
+            dist.all_gather_into_tensor(xyz_full, xyz_own_dev)
+            e[1].record()
+            ev.set_coords(xyz_full[:3 * n].view(n, 3))
+            st.check(L.jme_eval_device(st.h, 1, C.c_void_p(out_full.data_ptr())))
+            e[2].record()
+            dist.all_reduce(out_full[:10])
+            e[3].record()
+            dist.reduce_scatter_tensor(grad_own, out_full[10:])
+            e[4].record()
+            torch.cuda.synchronize()
+            for i in range(4):
+                acc[i] += e[i].elapsed_time(e[i + 1])
+        t = torch.tensor(acc, dtype=torch.float64, device=dev) / n_ph
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        phases = {k: float(v) for k, v in zip(names, t.tolist())}
+        phases["unit"] = "ms, max over ranks, measured in a separate loop after the timed region"
+
     # ---- end to end through the host-buffer C ABI (rank-local; for N > 1 the partial results are reduced
     #      on the device and copied back, so the host round trip is included on every rank)
     host_xyz = torch.from_numpy(system.xyz.copy()).pin_memory()
@@ -457,6 +484,7 @@ def main():
                        "cutoff": cfg["cutoff"], "path": cfg["path"], "parallelism": (f"atom-row shards x{world}; all-gather of coordinates, all-reduce of energies, "
                                        f"reduce-scatter of the gradient (every rank ends with the rows of its own atoms)")
                        if world > 1 else "single GPU",
+                       "scheme": {1: "all-pairs tiles", 3: "cell lists, per-atom survivor lists", 4: "cell lists, cluster lists + Newton's third law"}.get(int(L.jme_active_path(st.h)), "?"),
                        "l2": "256 MiB written between timed steps (L2 flush); step = marshal + cell build + pairs + bonded + reduce"},
             "e2e": {"value": pairs / (e2e_s / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": 24 * ev.chunk * world,
                     "d2h_bytes_per_step": (24 * ev.chunk + 80) * world, "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps},
@@ -464,7 +492,8 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_tflops, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp64_tflops, "traffic": traffic,
-                         "kernel": "cells_pair_kernel<GRAD>" if cfg["path"] == "cells" else "ap_kernel<GRAD>",
+                         "kernel": {1: "ap_kernel<GRAD>", 3: "cells_pair_kernel<GRAD> (per-atom lists)",
+                                    4: "cl_pair_kernel<4,GRAD> (cluster lists, Newton's third law)"}.get(int(L.jme_active_path(st.h)), "?"),
                          "kernel_ms": nb_ms, "build_ms": build_ms,
                          "peak_source": f"DFMA chain microbenchmark measured in this run ({fp64_mhz:.0f} MHz equivalent at 64 FMA/clk/SM); "
                                         "MEASURED_PEAKS.json has no FP64 figure",
@@ -478,6 +507,8 @@ def main():
         if parity is not None:
             line["parity"] = parity
             line["parity_checked"] = True
+        if phases is not None:
+            line["phases_ms"] = phases
         if not args.no_cpu_baseline:
             base, _, _ = cpu_baseline(args.workload, faithful=False)
             line["cpu_baseline"] = base

@@ -53,8 +53,11 @@ enum { JME_BOND = 0, JME_ANGLE = 1, JME_STRETCH_BEND = 2, JME_OOP = 3, JME_TORSI
        JME_N_COMPONENTS = 7 };
 
 /* Nonbonded path selection (jme_set_path). AUTO: all-pairs tiles when cutoff <= 0 or the
- * system is small, cell-list path otherwise. */
-typedef enum { JME_PATH_AUTO = 0, JME_PATH_ALLPAIRS = 1, JME_PATH_CELLS = 2 } jme_path;
+ * system is small, cell-list path otherwise.  The cell-list path has two evaluation schemes, chosen by
+ * size under JME_PATH_CELLS: per-atom survivor lists (small systems) and cluster lists with Newton's third
+ * law (large systems); the last two values force one of them (tests, tuning). */
+typedef enum { JME_PATH_AUTO = 0, JME_PATH_ALLPAIRS = 1, JME_PATH_CELLS = 2, JME_PATH_CELLS_LISTS = 3,
+               JME_PATH_CELLS_CLUSTERS = 4 } jme_path;
 
 /*
  * Everything MMFF94.assignParameters leaves on the container, flattened.  All tabulated
@@ -107,6 +110,9 @@ const char* jme_last_error(const jme_handle_t* h);
 /* cutoff <= 0 means unlimited, dielectric > 0 (ForceField.java:162-210). */
 int jme_set_options(jme_handle_t* h, double cutoff, double dielectric, int energy_unit);
 int jme_set_path(jme_handle_t* h, int path);
+/* The scheme the last evaluation used: JME_PATH_ALLPAIRS, JME_PATH_CELLS_LISTS or JME_PATH_CELLS_CLUSTERS
+ * (JME_PATH_AUTO before the first evaluation). */
+int jme_active_path(const jme_handle_t* h);
 
 /* Atom-row sharding for multi-GPU runs: this handle evaluates rank `rank` of `world` shares of the
  * nonbonded rows and bonded terms; the caller sums energies and gradients over ranks (all-reduce). */

@@ -23,7 +23,7 @@ JME_ERR_UNSUPPORTED = -5
 
 ENERGY_UNITS = {"KCAL_PER_MOL": 0, "KJ_PER_MOL": 1, "JOULE_PER_MOL": 2}
 COMPONENTS = ("bond", "angle", "stretch_bend", "oop", "torsion", "vdw", "ele")
-PATHS = {"auto": 0, "allpairs": 1, "cells": 2}
+PATHS = {"auto": 0, "allpairs": 1, "cells": 2, "cells-lists": 3, "cells-clusters": 4}
 
 
 class JmeSystem(C.Structure):

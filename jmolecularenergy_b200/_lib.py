@@ -21,7 +21,7 @@ EXPORTS = (
     "jme_energy", "jme_energy_gradient", "jme_pair_stats", "jme_pair_list", "jme_set_stream",
     "jme_set_coords_device", "jme_eval_device", "jme_eval_out_size", "jme_launch_count",
     "jme_measure_fp64_peak", "jme_enumerate_terms", "jme_exclusions", "jme_set_profiling", "jme_profile_read",
-    "jme_gd_minimize", "jme_adam_minimize",
+    "jme_gd_minimize", "jme_adam_minimize", "jme_active_path",
 )
 
 _lib = None
@@ -53,6 +53,8 @@ def lib():
     L.jme_set_options.argtypes = [H, C.c_double, C.c_double, C.c_int]
     L.jme_set_path.restype = C.c_int
     L.jme_set_path.argtypes = [H, C.c_int]
+    L.jme_active_path.restype = C.c_int
+    L.jme_active_path.argtypes = [H]
     L.jme_set_shard.restype = C.c_int
     L.jme_set_shard.argtypes = [H, C.c_int, C.c_int]
     L.jme_set_coords.restype = C.c_int

@@ -325,9 +325,13 @@ int build_bonded_plan(jme_handle* h) {
     return dev_alloc(h, &h->d_bpart, 5 * (size_t)std::max(1, h->n_bpart));
 }
 
+// atoms from which the cutoff path evaluates cluster lists with Newton's third law instead of per-atom lists (below,
+// the sweep of a few hundred segments leaves most of the chip idle; measured crossover)
+constexpr int64_t kClusterPathMinAtoms = 150000;
+
 int choose_path(const jme_handle* h) {
     if (h->path == JME_PATH_ALLPAIRS) return JME_PATH_ALLPAIRS;
-    if (h->path == JME_PATH_CELLS) return JME_PATH_CELLS;
+    if (h->path == JME_PATH_CELLS || h->path == JME_PATH_CELLS_LISTS || h->path == JME_PATH_CELLS_CLUSTERS) return JME_PATH_CELLS;
     // AUTO: the cell path pays off once the cutoff sphere holds a small fraction of the atoms
     if (h->cutoff > 0 && h->hs.n >= 6000) return JME_PATH_CELLS;
     return JME_PATH_ALLPAIRS;
@@ -341,11 +345,19 @@ int ensure_plan(jme_handle* h) {
     if (p == JME_PATH_ALLPAIRS) {
         if ((rc = build_allpairs_plan(h))) return rc;
     } else {
-        // JME_CLUSTER (development knob): atoms per cluster of the cutoff path, 2 or 4; 0 = the round-1 per-atom lists
-        int cluster = 4;
-        if (const char* e = std::getenv("JME_CLUSTER")) cluster = std::atoi(e);
-        if (cluster != 0 && cluster != 2 && cluster != 4) cluster = 4;
-        if (h->cells.built && h->cells.cluster != cluster) cluster = h->cells.cluster;
+        // the two evaluation schemes of the cutoff path: cluster lists (4 atoms per cluster) for large systems,
+        // per-atom lists below; JME_PATH_CELLS_LISTS / _CLUSTERS force one, JME_CLUSTER (0, 2, 4) is a development knob
+        int cluster = h->hs.n >= kClusterPathMinAtoms ? 4 : 0;
+        if (h->path == JME_PATH_CELLS_LISTS) cluster = 0;
+        if (h->path == JME_PATH_CELLS_CLUSTERS) cluster = 4;
+        if (const char* e = std::getenv("JME_CLUSTER")) {
+            const int v = std::atoi(e);
+            if (v == 0 || v == 2 || v == 4) cluster = v;
+        }
+        if (h->cells.built && h->cells.cluster != cluster) {          // the plan changes its kind: release the old one
+            for (void* q : h->cells.all_allocs) dev_free(h, q);
+            h->cells = CellPlan();
+        }
         rc = build_cell_plan(h->cells, h->hs, h->ds, h->cutoff, h->rank, h->world, cluster, h->err);
         for (void* q : h->cells.take_new_allocs()) h->mem.ptrs.push_back(q);
         if (rc) return rc;
@@ -702,10 +714,17 @@ int jme_set_options(jme_handle_t* h, double cutoff, double dielectric, int energ
 }
 
 int jme_set_path(jme_handle_t* h, int path) {
-    if (!h || path < 0 || path > 2) return JME_ERR_INVALID;
+    if (!h || path < 0 || path > JME_PATH_CELLS_CLUSTERS) return JME_ERR_INVALID;
     if (path != h->path) h->plan_dirty = true;
     h->path = path;
     return JME_OK;
+}
+
+int jme_active_path(const jme_handle_t* h) {
+    if (!h) return JME_ERR_INVALID;
+    if (h->plan_dirty) return JME_PATH_AUTO;
+    if (h->active_path == JME_PATH_ALLPAIRS) return JME_PATH_ALLPAIRS;
+    return h->cells.cluster != 0 ? JME_PATH_CELLS_CLUSTERS : JME_PATH_CELLS_LISTS;
 }
 
 int jme_set_shard(jme_handle_t* h, int rank, int world) {

@@ -600,12 +600,12 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 //   * nothing else in a trip takes a long-latency scoreboard: the partner's type comes with the list entry,
 //     exclusions are compared as sorted positions, the next atom's exclusion row is fetched a whole atom ahead.
 // Every pair is evaluated from both of its atoms: the gradient of i stays in registers, no scatter, no atomics.
-template <bool GRAD, bool EMIT>
+template <bool GRAD, bool EMIT, bool TSM>
 __global__ void __launch_bounds__(kCellThreads, JME_CELL_MIN_BLOCKS)
 cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PairConst* s_table = reinterpret_cast<PairConst*>(smem_raw);
-    const int TT = S.n_types * S.n_types;
+    const int TT = TSM ? S.n_types * S.n_types : 0;       // a table too large for shared memory is read through the caches
     GroupAtom* s_atoms = reinterpret_cast<GroupAtom*>(s_table + TT);               // 32-byte aligned
     unsigned int* s_ring = reinterpret_cast<unsigned int*>(s_atoms + kCellWarps * 32);
     unsigned int* s_excl = s_ring + kCellWarps * kRingSlots * kChunk;
@@ -669,7 +669,8 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
         int n_hits = 0, n_excl = 0, oi = 0, i = base;
         long long eb = 0;
         double pix = 0, piy = 0, piz = 0, qi2 = 0;
-        const PairConst* trow = s_table;
+        const PairConst* tbase = TSM ? s_table : S.table;
+        const PairConst* trow = tbase;
         double gix = 0, giy = 0, giz = 0;
         unsigned int n_eval = 0;
         // exclusion row of the NEXT atom, fetched one atom ahead (first atom: now)
@@ -708,7 +709,7 @@ cells_pair_kernel(DeviceSystem S, CellArrays C, CellPairArgs P) {
                 if (!kHasExcl) n_excl = 0;
                 pix = a.p.x; piy = a.p.y; piz = a.p.z;
                 qi2 = 2.0 * S.ele_scale * a.p.q;                            // doubled energies, see pair_terms
-                trow = s_table + a.t * S.n_types;
+                trow = tbase + a.t * S.n_types;
                 gix = giy = giz = 0;
                 if (kHasExcl) {
                     if (n_excl > 0) {
@@ -874,6 +875,7 @@ struct CellPlan {
     uint2* d_cellmask = nullptr;   // [max_cells] which force slots were written for a cell (cl_cellmask_kernel)
     unsigned int* d_layout = nullptr;   // [max_cells][16] window layout per segment (cl_layout_kernel)
     std::vector<void*> new_allocs;
+    std::vector<void*> all_allocs;         // everything the plan allocated (released when the plan changes its kind)
 
     std::vector<void*> take_new_allocs() { std::vector<void*> v; v.swap(new_allocs); return v; }
     void coords_changed() { sorted_valid = false; }
@@ -885,6 +887,7 @@ inline bool cell_alloc(CellPlan& p, T** out, size_t count, std::string& err) {
     cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
     if (e != cudaSuccess) { err = std::string("cudaMalloc (cell path): ") + cudaGetErrorString(e); return false; }
     p.new_allocs.push_back(q);
+    p.all_allocs.push_back(q);
     *out = static_cast<T*>(q);
     return true;
 }
@@ -904,10 +907,6 @@ inline int build_cell_plan(CellPlan& p, const HostSystem& hs, const DeviceSystem
     if ((long long)n * std::max(1, cluster) > 0x7fffff00ll) {
         err = "cell path: too many atoms for 32-bit sorted positions";
         return JME_ERR_UNSUPPORTED;
-    }
-    if (p.built && p.cluster != cluster) {
-        err = "internal: the cell plan cannot change its cluster size";
-        return JME_ERR_INVALID;
     }
     if (!p.built) {
         CellArrays& a = p.arr;
@@ -995,9 +994,24 @@ inline int build_cell_plan(CellPlan& p, const HostSystem& hs, const DeviceSystem
     return JME_OK;
 }
 
+inline bool cells_table_in_smem(const DeviceSystem& ds) { return (size_t)ds.n_types * ds.n_types * sizeof(PairConst) <= 48 * 1024; }
 inline size_t cells_smem_bytes(const DeviceSystem& ds) {
-    return (size_t)ds.n_types * ds.n_types * sizeof(PairConst) +
+    return (cells_table_in_smem(ds) ? (size_t)ds.n_types * ds.n_types * sizeof(PairConst) : 0) +
            kCellWarps * (32 * sizeof(GroupAtom) + (kExclSmem + kRingSlots * kChunk) * sizeof(unsigned int));
+}
+
+template <bool GRAD, bool EMIT>
+inline void launch_cells_pair(CellPlan& p, const DeviceSystem& ds, const CellPairArgs& P, cudaStream_t st) {
+    const size_t smem = cells_smem_bytes(ds);
+    if (cells_table_in_smem(ds)) {
+        auto k = cells_pair_kernel<GRAD, EMIT, true>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<p.grid_pairs, kCellThreads, smem, st>>>(ds, p.arr, P);
+    } else {
+        auto k = cells_pair_kernel<GRAD, EMIT, false>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<p.grid_pairs, kCellThreads, smem, st>>>(ds, p.arr, P);
+    }
 }
 
 #define JME_CELL_CHECK()                                                                           \
@@ -1069,16 +1083,8 @@ inline int run_cell_path(CellPlan& p, const DeviceSystem& ds, bool grad, cudaStr
     CellPairArgs P{};
     fill_pair_args(p, P);
     cudaMemsetAsync(p.arr.work_ctr + 1, 0, sizeof(int), st);
-    const size_t smem = cells_smem_bytes(ds);
-    if (grad) {
-        auto k = cells_pair_kernel<true, false>;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<<<p.grid_pairs, kCellThreads, smem, st>>>(ds, p.arr, P);
-    } else {
-        auto k = cells_pair_kernel<false, false>;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<<<p.grid_pairs, kCellThreads, smem, st>>>(ds, p.arr, P);
-    }
+    if (grad) launch_cells_pair<true, false>(p, ds, P, st);
+    else launch_cells_pair<false, false>(p, ds, P, st);
     ++launches;
     JME_CELL_CHECK();
     return JME_OK;
@@ -1094,10 +1100,7 @@ inline int run_cell_pairlist(CellPlan& p, const DeviceSystem& ds, int* d_i, int*
     fill_pair_args(p, P);
     P.out_i = d_i; P.out_j = d_j; P.out_14 = d_f; P.capacity = capacity; P.cursor = d_cursor;
     cudaMemsetAsync(p.arr.work_ctr + 1, 0, sizeof(int), st);
-    const size_t smem = cells_smem_bytes(ds);
-    auto k = cells_pair_kernel<false, true>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<p.grid_pairs, kCellThreads, smem, st>>>(ds, p.arr, P);
+    launch_cells_pair<false, true>(p, ds, P, st);
     ++launches;
     JME_CELL_CHECK();
     return JME_OK;

@@ -40,7 +40,7 @@ constexpr int kClMaxRows = 13;        // rows of the half shell at reach 2
 constexpr int kClMaxSegLen = 12;      // cells per segment (GridParams::seg_len is clamped to this in grid_setup_kernel)
 constexpr int kClRowPitch = 16;       // row-table entries per cell
 constexpr int kClBatch = 32;          // clusters staged per batch
-constexpr int kClWarps = 8;           // warps per CTA, one CTA per SM (255 registers per thread)
+constexpr int kClWarps = 8;           // warps per CTA, one CTA per SM (about 240 registers per thread; 12 warps at 168 registers were measured no faster)
 constexpr int kClMaxRing = 128;       // upper bound of the window slots per neighbour row (11 slot bits: 13 * 128 + 1)
 
 // 64-bit list entry: .x = sorted position of the partner, .y = meta
@@ -392,10 +392,10 @@ __device__ __forceinline__ void warp_multi_sum(double (&v)[N], int lane) {
 
 // per-warp shared memory: the force window (3 planes of kClMaxRows * ring + 8 doubles: the extra ones hold the dummy
 // slot of lanes beyond the end of a list), the row table and the batch's cluster data
-__host__ __device__ constexpr size_t cl_window_plane(int ring) { return (size_t)kClMaxRows * ring + 8; }
+__host__ __device__ constexpr size_t cl_window_plane(int pool) { return (size_t)pool + 8; }
 constexpr int kClNextBytes = 2 * (4 * 32 + 16);   // the current and the next cluster's atoms (C records + C types), ping-pong
-__host__ __device__ constexpr size_t cl_warp_smem(bool grad, int ring) {
-    return (grad ? 3 * cl_window_plane(ring) * sizeof(double) : 0) + kClMaxSegLen * kClRowPitch * sizeof(int) +
+__host__ __device__ constexpr size_t cl_warp_smem(bool grad, int pool) {
+    return (grad ? 3 * cl_window_plane(pool) * sizeof(double) : 0) + kClMaxSegLen * kClRowPitch * sizeof(int) +
            2 * kClBatch * sizeof(int) + kClNextBytes;
 }
 
@@ -815,7 +815,7 @@ cl_cellmask_kernel(CellArrays A, int rank, int world, uint2* __restrict__ mask) 
     }
 }
 
-__global__ void __launch_bounds__(kReduceWarps * 32)
+__global__ void __launch_bounds__(kReduceWarps * 32, 3)
 cl_reduce_kernel(CellArrays A, ClReduceArgs Q) {
     const GridParams& g = *A.grid;
     if (blockIdx.x == gridDim.x - 1) {
@@ -844,16 +844,20 @@ cl_reduce_kernel(CellArrays A, ClReduceArgs Q) {
         const unsigned int pa = (m.x >> 29) & 1u, pb = (m.x >> 30) & 1u;
         double gx = 0, gy = 0, gz = 0;
         if (m.x >> 31) { gx = Q.gi[3 * (size_t)p]; gy = Q.gi[3 * (size_t)p + 1]; gz = Q.gi[3 * (size_t)p + 2]; }
-        // the slot loads of an atom are independent: issue them together (predicated), then sum in row order
-        double vx[kClMaxRows], vy[kClMaxRows], vz[kClMaxRows];
+        // the slot loads of an atom are independent: issue them in two batches (predicated), sum in row order
 #pragma unroll
-        for (int o = 0; o < kClMaxRows; ++o) {
-            const double* src = Q.gj + ((size_t)(2 * o + pa) * np + p) * 3;
-            const bool u = (m.x >> o) & 1u;
-            vx[o] = u ? src[0] : 0.0; vy[o] = u ? src[1] : 0.0; vz[o] = u ? src[2] : 0.0;
+        for (int o0 = 0; o0 < kClMaxRows; o0 += 7) {
+            double vx[7], vy[7], vz[7];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                const int o = o0 + i;
+                const double* src = Q.gj + ((size_t)(2 * o + pa) * np + p) * 3;
+                const bool u = o < kClMaxRows && ((m.x >> o) & 1u);
+                vx[i] = u ? src[0] : 0.0; vy[i] = u ? src[1] : 0.0; vz[i] = u ? src[2] : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < 7; ++i) { gx += vx[i]; gy += vy[i]; gz += vz[i]; }
         }
-#pragma unroll
-        for (int o = 0; o < kClMaxRows; ++o) { gx += vx[o]; gy += vy[o]; gz += vz[o]; }
         for (unsigned int v = m.y & 0x1fffu; v; v &= v - 1) {     // cells next to a segment boundary: the second writer
             const double* src = Q.gj + ((size_t)(2 * (__ffs(v) - 1) + pb) * np + p) * 3;
             gx += src[0]; gy += src[1]; gz += src[2];

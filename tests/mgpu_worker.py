@@ -23,8 +23,9 @@ def main():
     from jmolecularenergy_b200 import systems
     from jmolecularenergy_b200.distributed import ShardedMMFF94, unpack
     from oracle import oracle
-    cases = [("solvated-6k cells", systems.solvated_chains(6000, exact_cutoff_pairs=40, cutoff=9.0), 9.0, "cells"),
-             ("ions-27k cells", systems.ion_box(30), 10.0, "cells"),
+    cases = [("solvated-6k cluster lists", systems.solvated_chains(6000, exact_cutoff_pairs=40, cutoff=9.0), 9.0, "cells-clusters"),
+             ("ions-27k per-atom lists", systems.ion_box(30), 10.0, "cells-lists"),
+             ("ions-27k cluster lists", systems.ion_box(30), 10.0, "cells-clusters"),
              ("water-900 all pairs", systems.water_box(300), 0.0, "allpairs")]
     worst = {"energy": 0.0, "gradient": 0.0}
     ok = True

@@ -16,6 +16,8 @@ PINNED = golden_names()
 ALL = golden_names(pinned_only=False)
 E_RTOL = 1e-10
 G_RTOL = 1e-8
+# the two evaluation schemes of the cutoff path (per-atom lists / cluster lists with Newton's third law); "cells" picks by size
+CELL_PATHS = ("cells-lists", "cells-clusters")
 
 
 def gpu_ff(path="auto", cutoff=0.0, dielectric=1.0, unit=None):
@@ -106,7 +108,7 @@ def test_config2_water_3k(oracle):
     assert_parity(got, ref, s.name)
 
 
-@pytest.mark.parametrize("path", ["allpairs", "cells"])
+@pytest.mark.parametrize("path", ["allpairs", *CELL_PATHS])
 @pytest.mark.parametrize("cutoff", [6.0, 9.5])
 def test_cutoff_paths_small(oracle, path, cutoff):
     from jmolecularenergy_b200 import systems
@@ -145,11 +147,12 @@ def test_config3_solvated_25k(oracle, cutoff):
     the reference-faithful evaluator in tests/test_oracle_fast.py)."""
     from jmolecularenergy_b200 import systems
     s = systems.solvated_chains(24999, exact_cutoff_pairs=100, cutoff=cutoff)
-    ff = gpu_ff(cutoff=cutoff)
-    ff.assignParameters(s)
-    got = ff.calculateComponents(s, gradient=True)
     ref = oracle.fast_evaluate(s, cutoff=cutoff)
-    assert_parity(got, ref, s.name)
+    for path in ("auto", *CELL_PATHS):
+        ff = gpu_ff(path=path, cutoff=cutoff)
+        ff.assignParameters(s)
+        got = ff.calculateComponents(s, gradient=True)
+        assert_parity(got, ref, f"{s.name} {path}")
     # the all-pairs tiles with the cutoff predicate must select the same pairs and agree to rounding
     ff2 = gpu_ff(path="allpairs", cutoff=cutoff)
     ff2.assignParameters(s)
@@ -162,11 +165,11 @@ def test_config3_solvated_25k(oracle, cutoff):
 def test_config5_ion_box_125k(oracle):
     from jmolecularenergy_b200 import systems
     s = systems.ion_box(50)
-    ff = gpu_ff(cutoff=10.0)
-    ff.assignParameters(s)
-    got = ff.calculateComponents(s, gradient=True)
     ref = oracle.fast_evaluate(s, cutoff=10.0)
-    assert_parity(got, ref, s.name)
+    for path in CELL_PATHS:
+        ff = gpu_ff(path=path, cutoff=10.0)
+        ff.assignParameters(s)
+        assert_parity(ff.calculateComponents(s, gradient=True), ref, f"{s.name} {path}")
 
 
 def test_config5_ion_box_1m_properties(oracle):
@@ -175,15 +178,17 @@ def test_config5_ion_box_1m_properties(oracle):
     a 2-way shard sum equal to the unsharded result."""
     from jmolecularenergy_b200 import systems
     s = systems.ion_box(100)
-    ff = gpu_ff(cutoff=10.0)
-    ff.assignParameters(s)
-    a = ff.calculateComponents(s, gradient=True)
-    b = ff.calculateComponents(s, gradient=True)
-    assert a["total"] == b["total"] and np.array_equal(a["gradient"], b["gradient"])
-    net = np.abs(a["gradient"].sum(axis=0)).max()
-    assert net <= 1e-9 * np.abs(a["gradient"]).sum()
     ref = oracle.fast_evaluate(s, cutoff=10.0, gradient=True)
-    assert_parity(a, ref, s.name)
+    for path in ("auto", "cells-lists"):             # auto = the cluster lists at this size
+        ff = gpu_ff(path=path, cutoff=10.0)
+        ff.assignParameters(s)
+        a = ff.calculateComponents(s, gradient=True)
+        b = ff.calculateComponents(s, gradient=True)
+        assert a["total"] == b["total"] and np.array_equal(a["gradient"], b["gradient"]), path
+        net = np.abs(a["gradient"].sum(axis=0)).max()
+        assert net <= 1e-9 * np.abs(a["gradient"]).sum()
+        assert_parity(a, ref, f"{s.name} {path}")
+        ff.release(s)
 
 
 def test_units_and_dielectric(oracle):
@@ -248,7 +253,8 @@ def test_two_way_shard_sums_to_unsharded(oracle):
     from jmolecularenergy_b200 import systems, _lib
     from jmolecularenergy_b200.forcefield import _GpuState
     import torch
-    for s, cutoff, path in ((systems.water_box(200), 0.0, 1), (systems.solvated_chains(3000, chain_fraction=0.3), 8.0, 2)):
+    for s, cutoff, path in ((systems.water_box(200), 0.0, 1), (systems.solvated_chains(3000, chain_fraction=0.3), 8.0, 3),
+                            (systems.solvated_chains(3000, chain_fraction=0.3), 8.0, 4), (systems.ion_box(24), 9.0, 4)):
         L = _lib.lib()
         full = None
         parts = []
@@ -471,7 +477,7 @@ def _star_in_ion_bath(n_leaves=70, n_side=9):
         name=f"star{n_leaves}-in-ions")
 
 
-@pytest.mark.parametrize("path", ["allpairs", "cells"])
+@pytest.mark.parametrize("path", ["allpairs", *CELL_PATHS])
 def test_exclusion_rows_longer_than_the_shared_buffer(oracle, path):
     s = _star_in_ion_bath()
     ff = gpu_ff(path=path, cutoff=9.0)
@@ -483,13 +489,14 @@ def test_exclusion_rows_longer_than_the_shared_buffer(oracle, path):
     assert np.array_equal(pi, oi) and np.array_equal(pj, oj) and np.array_equal(f14, of)
 
 
-def test_cell_path_coincident_atoms_and_long_lists(oracle):
+@pytest.mark.parametrize("cells", CELL_PATHS)
+def test_cell_path_coincident_atoms_and_long_lists(oracle, cells):
     """Two ions on the same point (r = 0: finite buffered energy, no gradient direction) and a dense cluster
     whose survivor lists span several 128-entry chunks, through the cell path."""
     from jmolecularenergy_b200 import systems
     s = systems.ion_box(12, spacing=1.7)           # ~2x liquid density: ~850 partners within 10 A
     s.xyz[701] = s.xyz[64]
-    ff = gpu_ff(path="cells", cutoff=10.0)
+    ff = gpu_ff(path=cells, cutoff=10.0)
     ff.assignParameters(s)
     got = ff.calculateComponents(s, gradient=True)
     ref = oracle.evaluate(s, cutoff=10.0, gradient=True)
@@ -503,19 +510,20 @@ def test_cell_path_coincident_atoms_and_long_lists(oracle):
     np.testing.assert_allclose(got["gradient"][ok], g_ref[ok], rtol=G_RTOL, atol=floor)
 
 
-def test_cell_path_grows_its_lists_for_dense_systems(oracle):
+@pytest.mark.parametrize("cells", CELL_PATHS)
+def test_cell_path_grows_its_lists_for_dense_systems(oracle, cells):
     """More partners inside the cutoff sphere than the initial survivor-list capacity (1024): the host API grows
     the lists and re-evaluates; a device-side caller of a fresh handle sees a poisoned (NaN) total, never a
     silently truncated sum."""
     from jmolecularenergy_b200 import systems
     from jmolecularenergy_b200.distributed import ShardedMMFF94, unpack
     s = systems.ion_box(13, spacing=1.7)           # 0.2 atoms/A^3: ~1450 partners within 12 A
-    ev = ShardedMMFF94(s, cutoff=12.0, path="cells", rank=0, world=1)
+    ev = ShardedMMFF94(s, cutoff=12.0, path=cells, rank=0, world=1)
     ev.set_coords(s.xyz)
     raw = ev.evaluate(gradient=True)
     ev.close()
     assert np.isnan(raw["total"])
-    ff = gpu_ff(path="cells", cutoff=12.0)
+    ff = gpu_ff(path=cells, cutoff=12.0)
     ff.assignParameters(s)
     got = ff.calculateComponents(s, gradient=True)
     ref = oracle.evaluate(s, cutoff=12.0, gradient=True)
@@ -541,7 +549,7 @@ def test_random_systems_both_cutoff_paths(oracle, seed):
     cutoff = float(rng.uniform(3.5, 11.0))
     ref = oracle.evaluate(s, cutoff=cutoff, gradient=True) if s.n_atoms <= 1200 else \
         oracle.fast_evaluate(s, cutoff=cutoff, gradient=True)
-    for path in ("cells", "allpairs"):
+    for path in (*CELL_PATHS, "allpairs"):
         ff = gpu_ff(path=path, cutoff=cutoff)
         ff.assignParameters(s)
         got = ff.calculateComponents(s, gradient=True)
@@ -560,15 +568,16 @@ def test_cell_path_non_finite_coordinates_poison_the_total_and_return():
     out of bounds - it returns with a NaN total (the edge-growth loop used to spin for ever)."""
     from jmolecularenergy_b200 import systems
     for bad in (np.inf, -np.inf, np.nan, -np.nan):
-        s = systems.water_box(120)
-        s.xyz[17, 1] = bad
-        ff = gpu_ff(path="cells", cutoff=7.0)
-        ff.assignParameters(s)
-        got = ff.calculateComponents(s, gradient=True)
-        assert np.isnan(got["total"]), bad
-        # and the handle is still usable afterwards
-        s.xyz[17, 1] = 3.25
-        assert np.isfinite(ff.calculateEnergy(s))
+        for cells in CELL_PATHS:
+            s = systems.water_box(120)
+            s.xyz[17, 1] = bad
+            ff = gpu_ff(path=cells, cutoff=7.0)
+            ff.assignParameters(s)
+            got = ff.calculateComponents(s, gradient=True)
+            assert np.isnan(got["total"]), (bad, cells)
+            # and the handle is still usable afterwards
+            s.xyz[17, 1] = 3.25
+            assert np.isfinite(ff.calculateEnergy(s))
 
 
 @pytest.mark.parametrize("cutoff,x1,x2", [(6.0, 2.9999999999999996, 9.0), (10.0, 4.999999999999999, 15.0)])
@@ -585,7 +594,7 @@ def test_cell_boundary_pair_at_exactly_the_cutoff(oracle, cutoff, x1, x2):
     assert np.sqrt((x2 - x1) ** 2) == cutoff
     oi, oj, of = oracle.pair_list(s, cutoff=cutoff)
     assert np.any((oi == 1) & (oj == 2))
-    for path in ("cells", "allpairs"):
+    for path in (*CELL_PATHS, "allpairs"):
         ff = gpu_ff(path=path, cutoff=cutoff)
         ff.assignParameters(s)
         pi, pj, f14 = ff.pairList(s)
@@ -608,7 +617,7 @@ def test_cell_path_many_atom_types_table_outside_shared_memory(oracle):
         vdw_G=rng.uniform(0.8, 1.4, len(types)).astype(np.float32), vdw_DA=rng.integers(0, 3, len(types)).astype(np.uint8),
         name="ions-90-types")
     ref = oracle.evaluate(s, cutoff=8.0, gradient=True)
-    for path in ("cells", "allpairs"):
+    for path in (*CELL_PATHS, "allpairs"):
         ff = gpu_ff(path=path, cutoff=8.0)
         ff.assignParameters(s)
         assert_parity(ff.calculateComponents(s, gradient=True), ref, path)

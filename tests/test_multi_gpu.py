@@ -27,4 +27,4 @@ def test_owner_mode_under_torchrun_matches_the_oracle(world):
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "mgpu_worker.py")]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count('"ok": true') == 3 * world, r.stdout[-3000:]
+    assert r.stdout.count('"ok": true') == 4 * world, r.stdout[-3000:]
