@@ -321,6 +321,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the host entry points size the cutoff path's lists to the system (a device-side evaluation cannot: an overflow
+    # only poisons its total); one host-API energy before the device-resident loop does that on every rank
+    if world == 1:
+        ev.set_coords(xyz_dev)
+    else:
+        ev.set_coords_owned(xyz_own_dev, xyz_full)
+    ev.prime()
     for _ in range(args.warmup):
         step_device()
     barrier()
@@ -334,6 +341,7 @@ def main():
         ev1 = ShardedMMFF94(system, cutoff=cfg["cutoff"], path=cfg["path"], rank=0, world=1)
         out1 = ev1.new_output(True)
         ev1.set_coords(xyz_dev)
+        ev1.prime()
         ev1.evaluate_into(out1, True)
         torch.cuda.synchronize()
         ref1 = out1.cpu().numpy()

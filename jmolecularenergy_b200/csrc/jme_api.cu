@@ -108,7 +108,7 @@ struct jme_handle {
 };
 
 namespace {
-constexpr int kListOverflow = 1;       // internal: finish_host saw the overflow flag of the cell path
+constexpr int kListOverflow = 100;     // internal: finish_host saw an overflow flag of the cell path (+ 1: entries, + 2: clusters)
 
 #define JME_CUDA(h, call)                                                                        \
     do {                                                                                         \
@@ -551,43 +551,45 @@ int finish_host(jme_handle* h, bool grad, double* total, double* comps, double* 
     h->last_cand = (uint64_t)h->h_out[9];
     if (h->active_path == JME_PATH_CELLS && h->h_out[kOutHeader] != 0.0) {
         const int f = (int)h->h_out[kOutHeader];
-        if (f & 2) return fail(h, JME_ERR_UNSUPPORTED, "cell path: a cell row window holds more atoms than the list entry format addresses (density too high for this cutoff)");
-        if (f & 1) return kListOverflow;
+        if (f & 3) return kListOverflow + (f & 3);            // which storage ran out travels with the code
         // f & 4: a non-finite coordinate - the total is NaN, which is the answer
     }
     return JME_OK;
 }
 
 // after an overflow: survivor lists with twice the capacity per atom (the old ones are released), flag cleared
-int grow_cell_lists(jme_handle* h) {
+// replace a plan allocation (the plan's own bookkeeping follows)
+template <class T>
+int realloc_plan(jme_handle* h, T** p, size_t count) {
+    auto& all = h->cells.all_allocs;
+    all.erase(std::remove(all.begin(), all.end(), static_cast<void*>(*p)), all.end());
+    dev_free(h, *p);
+    *p = nullptr;
+    int rc = dev_alloc(h, p, count);
+    if (!rc) all.push_back(*p);
+    return rc;
+}
+
+// after an overflow: `what` bit 0 = a list was truncated (twice the entries per list), bit 1 = the sort produced more
+// clusters than the lists hold (twice the clusters); the old storage is released, the flags are cleared
+int grow_cell_lists(jme_handle* h, int what = 1) {
     CellPlan& p = h->cells;
-    const int cap = p.list_cap * 2;
-    const size_t count = (size_t)std::max(1, h->ds.n) * cap;
+    int cap = p.list_cap, ccap = p.cluster_cap;
+    if (what & 1) cap *= 2;
     if (cap > (1 << 16)) { h->err = "survivor-list capacity limit"; return JME_ERR_NOMEM; }
     int rc;
     if (p.cluster != 0) {
-        dev_free(h, p.d_clist);
-        p.d_clist = nullptr;
-        rc = dev_alloc(h, &p.d_clist, count);
-        if (rc) {            // keep the plan usable at the old capacity
-            std::string why = h->err;
-            if (dev_alloc(h, &p.d_clist, count / 2)) { p.built = false; h->plan_dirty = true; }
-            h->err = why;
-            return rc;
-        }
+        if (what & 2) ccap = std::min(std::max(1, h->ds.n), std::max(ccap + 1, ccap * 2));
+        rc = realloc_plan(h, &p.d_clist, (size_t)ccap * cap);
+        if (!rc && ccap != p.cluster_cap) rc = realloc_plan(h, &p.d_count, (size_t)ccap);
+        if (rc) { p.built = false; h->plan_dirty = true; return rc; }
+        p.cluster_cap = ccap;
     } else {
-        dev_free(h, p.d_list);
-        p.d_list = nullptr;
-        rc = dev_alloc(h, &p.d_list, count);
-        if (rc) {
-            std::string why = h->err;
-            if (dev_alloc(h, &p.d_list, count / 2)) { p.built = false; h->plan_dirty = true; }
-            h->err = why;
-            return rc;
-        }
+        rc = realloc_plan(h, &p.d_list, (size_t)std::max(1, h->ds.n) * cap);
+        if (rc) { p.built = false; h->plan_dirty = true; return rc; }
     }
     p.list_cap = cap;
-    JME_CUDA(h, cudaMemset(p.d_overflow, 0, sizeof(int)));
+    JME_CUDA(h, cudaMemset(p.arr.flags, 0, 4 * sizeof(int)));
     return JME_OK;
 }
 
@@ -598,9 +600,9 @@ int eval_host(jme_handle* h, bool grad, double* total, double* comps, double* gr
         int rc = enqueue_eval(h, grad, nullptr);
         if (rc) return rc;
         rc = finish_host(h, grad, total, comps, grad_xyz);
-        if (rc != kListOverflow) return rc;
+        if (rc <= kListOverflow) return rc;
         const int old_cap = h->cells.list_cap;
-        if (int g = grow_cell_lists(h)) {
+        if (int g = grow_cell_lists(h, rc - kListOverflow)) {
             if (g == JME_ERR_NOMEM) h->err = "a cutoff sphere holds more atoms than the survivor-list capacity (" +
                 std::to_string(old_cap) + ") and larger lists do not fit in device memory: " + h->err;
             return g;
@@ -984,8 +986,9 @@ int jme_pair_list(jme_handle_t* h, int32_t* pair_i, int32_t* pair_j, uint8_t* is
             rc = h->cells.cluster != 0
                      ? cl_run_pairlist(h->cells, h->ds, d_i, d_j, d_f, capacity, d_cur, h->stream, h->launches, h->err)
                      : run_cell_pairlist(h->cells, h->ds, d_i, d_j, d_f, capacity, d_cur, h->stream, h->launches, h->err);
-            if (rc || cudaStreamSynchronize(h->stream) != cudaSuccess || !cell_overflowed(h->cells)) break;
-            if ((rc = grow_cell_lists(h))) break;
+            int what = 0;
+            if (rc || cudaStreamSynchronize(h->stream) != cudaSuccess || !(what = cell_overflowed(h->cells))) break;
+            if ((rc = grow_cell_lists(h, what))) break;
             ++h->graph_epoch;
             cudaMemsetAsync(d_cur, 0, sizeof(unsigned long long), h->stream);
         }

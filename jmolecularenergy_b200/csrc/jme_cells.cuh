@@ -867,7 +867,8 @@ struct CellPlan {
     int sms = 148;
     int cl_warps = 0, cl_table_in_smem = 1;
     size_t cl_smem_grad = 0, cl_smem_energy = 0;
-    uint2* d_clist = nullptr;      // cluster lists: [clusters][list_cap] 64-bit entries
+    uint2* d_clist = nullptr;      // cluster lists: [cluster_cap][list_cap] 64-bit entries
+    int cluster_cap = 0;           // clusters the lists hold (grown with the lists when the sort produces more)
     double* d_gi = nullptr;
     double* d_gj = nullptr;
     double* d_gj_ovf = nullptr;
@@ -962,9 +963,11 @@ inline int build_cell_plan(CellPlan& p, const HostSystem& hs, const DeviceSystem
             p.n_epart = p.epart_cap = a.max_cells;
             if (!cell_alloc(p, &p.d_epart, 2 * (size_t)p.n_epart, err) || !cell_alloc(p, &p.d_cpart, 2 * (size_t)p.n_epart, err)) return JME_ERR_NOMEM;
             // cluster lists: one per cluster (every cluster holds at least one atom: <= n clusters)
-            p.list_cap = 384;
-            while (p.list_cap > 128 && (size_t)n * p.list_cap * sizeof(uint2) > ((size_t)24 << 30)) p.list_cap -= 64;
-            if (!cell_alloc(p, &p.d_clist, (size_t)std::max(1, n) * p.list_cap, err) || !cell_alloc(p, &p.d_count, std::max(1, n), err) ||
+            // about 290 entries per cluster of 4 at liquid density and 10 A; every cluster holds at least one atom, at
+            // liquid density about 3.6: room for n / 2 clusters to start with (both grow on overflow, jme_api.cu)
+            p.list_cap = 512;
+            p.cluster_cap = std::min(std::max(1, n), std::max(4096, n / 2));
+            if (!cell_alloc(p, &p.d_clist, (size_t)p.cluster_cap * p.list_cap, err) || !cell_alloc(p, &p.d_count, p.cluster_cap, err) ||
                 !cell_alloc(p, &p.d_gi, 3 * ns, err) || !cell_alloc(p, &p.d_gj, (size_t)2 * 13 * 3 * ns, err) ||
                 !cell_alloc(p, &p.d_gj_ovf, 3 * ns, err) || !cell_alloc(p, &p.d_excl_src, hs.excl_ent.size(), err) ||
                 !cell_alloc(p, &p.d_cellmask, (size_t)a.max_cells, err) || !cell_alloc(p, &p.d_layout, (size_t)16 * a.max_cells, err))
@@ -1106,11 +1109,12 @@ inline int run_cell_pairlist(CellPlan& p, const DeviceSystem& ds, int* d_i, int*
     return JME_OK;
 }
 
-// 1 if a survivor list overflowed its capacity since the flag was last cleared (results are then incomplete)
+// which list storage overflowed since the flags were last cleared (results are then incomplete):
+// bit 0 = the entries of a list, bit 1 = the number of clusters
 inline int cell_overflowed(CellPlan& p) {
-    int v = 0;
-    if (p.d_overflow) cudaMemcpy(&v, p.d_overflow, sizeof(int), cudaMemcpyDeviceToHost);
-    return v;
+    int v[4] = {0, 0, 0, 0};
+    if (p.arr.flags) cudaMemcpy(v, p.arr.flags, sizeof(v), cudaMemcpyDeviceToHost);
+    return (v[0] ? 1 : 0) | (v[3] ? 2 : 0);
 }
 
 }  // namespace jme

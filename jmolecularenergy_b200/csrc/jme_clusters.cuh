@@ -132,6 +132,7 @@ struct ClListArgs {
     uint2* list;                   // [clusters][cap]
     int* count;                    // [clusters]
     int cap;
+    int ccap;                      // clusters the list storage holds (more: overflow flag, the host grows and retries)
     int parts;                     // warps sharing one cell (small systems)
     int rank, world;
     const unsigned int* layout;    // [segments][16] ring of every half-shell row in the sweeping warp's window (cl_layout_kernel)
@@ -224,6 +225,10 @@ cl_list_kernel(CellArrays A, ClListArgs P) {
         for (int ch = a_begin; ch < a_end; ch += 32) {              // at most 32 atoms (32 / C clusters) at a time
             const int nc = min(32, a_end - ch);                       // multiple of C
             const int nq = nc / C;
+            if (ch / C + nq > P.ccap) {                               // more clusters than list storage
+                if (lane == 0) A.flags[3] = 1;
+                break;
+            }
             __syncwarp();
             {
                 const float4 f = fxyz[min(ch + lane, a_end - 1)];
@@ -327,7 +332,7 @@ cl_list_kernel(CellArrays A, ClListArgs P) {
 template <int C>
 __global__ void __launch_bounds__(256)
 cl_mark_kernel(CellArrays A, const int* __restrict__ excl_src, uint2* __restrict__ list, const int* __restrict__ count,
-               int cap, int rank, int world) {
+               int cap, int ccap, int rank, int world) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= A.n_excl_ent) return;
     const unsigned int x = A.sexcl_ent[k];
@@ -341,6 +346,7 @@ cl_mark_kernel(CellArrays A, const int* __restrict__ excl_src, uint2* __restrict
         if (ci < cl_seg_first_cell(g, s0) || ci >= cl_seg_first_cell(g, s1)) return;      // not this shard's list
     }
     const int q = si / C, a = si % C;
+    if (q >= ccap) return;
     uint2* lst = list + (size_t)q * cap;
     const int n = min(count[q], cap);
     int lo = 0, hi = n;
@@ -357,6 +363,7 @@ struct ClPairArgs {
     const uint2* list;             // [clusters][cap]
     const int* count;              // [clusters]
     int cap;
+    int ccap;                      // clusters the list storage holds
     int rank, world;
     int pool;                      // slots of a warp's force window (cl_layout_kernel shares them among the rows)
     const unsigned int* layout;    // [segments][16]
@@ -517,7 +524,7 @@ cl_pair_kernel(DeviceSystem S, CellArrays A, ClPairArgs P) {
             for (int qb = q0; qb < q1; qb += kClBatch) {
                 const int nq = min(kClBatch, q1 - qb);
                 __syncwarp();                                     // the previous batch's reads of s_cnt / s_ci are over
-                s_cnt[lane] = lane < nq ? min(P.count[qb + lane], P.cap) : 0;
+                s_cnt[lane] = lane < nq && qb + lane < P.ccap ? min(P.count[qb + lane], P.cap) : 0;
                 s_ci[lane] = lane < nq ? A.scell[C * (qb + lane)] - rowbase - xa : 0;
                 __syncwarp();
                 {   // the batch's first two lists on their way to L2
@@ -935,7 +942,7 @@ inline int cl_configure(CellPlan& p, const DeviceSystem& ds, std::string& err) {
 template <int C>
 inline int cl_run_lists_t(CellPlan& p, const DeviceSystem& ds, cudaStream_t st, uint64_t& launches, std::string& err) {
     ClListArgs A{};
-    A.list = p.d_clist; A.count = p.d_count; A.cap = p.list_cap; A.rank = p.rank; A.world = p.world;
+    A.list = p.d_clist; A.count = p.d_count; A.cap = p.list_cap; A.ccap = p.cluster_cap; A.rank = p.rank; A.world = p.world;
     A.layout = p.d_layout;
     const int grid = p.sms * kClListMinBlocks;
     const long long resident = (long long)grid * kListWarps;
@@ -947,7 +954,7 @@ inline int cl_run_lists_t(CellPlan& p, const DeviceSystem& ds, cudaStream_t st, 
     ++launches;
     if (p.arr.n_excl_ent > 0) {
         cl_mark_kernel<C><<<(unsigned int)((p.arr.n_excl_ent + 255) / 256), 256, 0, st>>>(p.arr, p.d_excl_src, p.d_clist, p.d_count,
-                                                                                        p.list_cap, p.rank, p.world);
+                                                                                        p.list_cap, p.cluster_cap, p.rank, p.world);
         ++launches;
     }
     JME_CELL_CHECK();
@@ -960,7 +967,7 @@ inline int cl_run_lists(CellPlan& p, const DeviceSystem& ds, cudaStream_t st, ui
 }
 
 inline void cl_fill_pair_args(CellPlan& p, ClPairArgs& P) {
-    P.list = p.d_clist; P.count = p.d_count; P.cap = p.list_cap;
+    P.list = p.d_clist; P.count = p.d_count; P.cap = p.list_cap; P.ccap = p.cluster_cap;
     P.rank = p.rank; P.world = p.world; P.n_spad = p.n_spad + 1; P.pool = p.arr.ring; P.layout = p.d_layout;
     P.gi = p.d_gi; P.gj = p.d_gj; P.gj_ovf = p.d_gj_ovf;
     P.epart = p.d_epart; P.cpart = p.d_cpart;

@@ -506,7 +506,7 @@ struct ReduceArgs {
     double* out_host;               // optional: mapped pinned host copy of the header (zero-copy result), kOutHeader + 1
                                     // doubles: [kOutHeader] = overflow flag
     const int* overflow;            // optional: the cell paths' device flags [4]: [0] a list was truncated, [1] non-finite
-                                    // coordinate, [2] window fallback used (informational), [3] density beyond the entry format
+                                    // coordinate, [2] window fallback used (informational), [3] more clusters than list storage
 };
 constexpr int kOutHeader = 10;
 
@@ -550,7 +550,7 @@ __device__ __forceinline__ void reduce_energy_block(const ReduceArgs& A) {
         }
         // a truncated survivor list means missing pairs: the total is poisoned (NaN) so that no caller - host or
         // device side, before or after an all-reduce - can mistake the result for a valid energy
-        // bit 0: retry with longer lists, bit 1: density beyond the entry format, bit 2: non-finite coordinate
+        // bit 0: retry with longer lists, bit 1: retry with storage for more clusters, bit 2: non-finite coordinate
         const int ovf = A.overflow ? ((A.overflow[0] ? 1 : 0) | (A.overflow[3] ? 2 : 0) | (A.overflow[1] ? 4 : 0)) : 0;
         A.out[0] = ovf ? __longlong_as_double(0x7ff8000000000000ll) : total;
         A.out[8] = (double)s_c[0][0];

@@ -101,6 +101,17 @@ class ShardedMMFF94:
             a = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1)
             st.check(self.L.jme_set_coords(st.h, a.ctypes.data, self.n))
 
+    def prime(self) -> None:
+        """One host-API energy evaluation of the coordinates set last (``jme_energy``): it is the host entry points
+        that size the cutoff path's lists to the system (a device-side evaluation whose lists overflow reports a NaN
+        total and leaves them as they are).  Call once after the first ``set_coords`` of a device-resident loop."""
+        if self.local_eval is not None:
+            return
+        st = self.state
+        total = C.c_double()
+        st.check(self.L.jme_energy(st.h, C.byref(total), None))
+        self._bind_stream()
+
     def evaluate_into(self, out, gradient: bool = True) -> None:
         """Enqueue the local evaluation and the all-reduce on the current stream; no host sync."""
         if self.local_eval is not None:

@@ -37,6 +37,8 @@ def main():
         xyz_full, out_full, grad_own = ev.new_owner_buffers()
         xyz_own = torch.zeros(3 * ev.chunk, dtype=torch.float64, device=dev)
         xyz_own[:3 * (a1 - a0)] = torch.from_numpy(s.xyz[a0:a1].reshape(-1)).to(dev)
+        ev.set_coords_owned(xyz_own, xyz_full)
+        ev.prime()                              # sizes the lists of the cutoff path (host entry point)
         for _ in range(2):                      # twice: the second evaluation replays the captured graph
             ev.set_coords_owned(xyz_own, xyz_full)
             ev.evaluate_owned_into(out_full, grad_own)

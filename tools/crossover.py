@@ -25,6 +25,8 @@ def main():
             ev = ShardedMMFF94(s, cutoff=10.0, path="cells", rank=0, world=1)
             xyz = torch.from_numpy(s.xyz).to(dev)
             out = ev.new_output(True)
+            ev.set_coords(xyz)
+            ev.prime()
             for _ in range(5):
                 ev.set_coords(xyz)
                 ev.evaluate_into(out, True)
