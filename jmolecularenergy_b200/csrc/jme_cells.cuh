@@ -56,6 +56,7 @@ struct GridParams {
     int seg_len;             // cells per segment along x (>= 2 reach + 1)
     int nsx;                 // segments per cell row
     int n_seg;               // ny * nz * nsx
+    int seg_lo, seg_hi;      // the segments of THIS shard (grid_setup_kernel: equal estimated pair work per rank)
 };
 
 // Cells whose atoms a shard of the cluster path touches: the cells of its segments plus the cells its force windows
@@ -64,7 +65,8 @@ struct GridParams {
 __device__ __forceinline__ void shard_cell_range(const GridParams& g, int rank, int world, int& c_lo, int& c_hi) {
     c_lo = 0; c_hi = g.ncell;
     if (world <= 1 || g.n_seg <= 0) return;
-    const long long s0 = (long long)g.n_seg * rank / world, s1 = (long long)g.n_seg * (rank + 1) / world;
+    (void)rank;
+    const long long s0 = g.seg_lo, s1 = g.seg_hi;
     auto first_cell = [&](long long s) { return s >= g.n_seg ? g.ncell : (int)(s / g.nsx) * g.nx + (int)(s % g.nsx) * g.seg_len; };
     c_lo = first_cell(s0);
     const long long last_row = (s1 + g.nsx - 1) / g.nsx;                       // one past the last row with a segment of the shard
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(256) bbox_kernel(DeviceSystem S, double* __res
 }
 
 __global__ void grid_setup_kernel(const double* __restrict__ part, int n_part, double cutoff, int max_cells, int seg_target,
-                                  GridParams* g) {
+                                  int rank, int world, GridParams* g) {
     // one warp: lanes stride over the per-block bounding boxes, shuffle min/max, lane 0 derives the grid
     const int lane = threadIdx.x;
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
@@ -198,6 +200,56 @@ __global__ void grid_setup_kernel(const double* __restrict__ part, int n_part, d
         g->nsx = (g->nx + len - 1) / len;
         g->n_seg = rows * g->nsx;
         g->n_half = g->reach * (2 * g->reach + 1) + g->reach + 1;
+        // The shard of this rank: segments [seg_lo, seg_hi).  The pair work of a segment is estimated by the rows of the
+        // half shell that exist for its cell row, weighted with their share of the pairs at uniform density (the rows
+        // at the far end of the box have no forward neighbours: equal segment COUNTS gave the last rank 15 % less work
+        // than the first).  Every rank computes the same boundaries.
+        g->seg_lo = (int)((long long)g->n_seg * rank / world);
+        g->seg_hi = (int)((long long)g->n_seg * (rank + 1) / world);
+        if (world > 1 && g->reach == 2 && g->ny >= 5 && g->nz >= 3) {
+            const int wt[13] = {122, 198, 54, 25, 135, 198, 135, 25, 1, 25, 54, 25, 1};    // tools/fill_experiment.py, per mille
+            const int ny = g->ny, nz = g->nz;
+            auto wrow = [&](int y, int z) {
+                int w = 0;
+                for (int o = 0; o < 13; ++o) {
+                    const int dy = o <= 2 ? o : (o - 3) % 5 - 2, dz = o <= 2 ? 0 : 1 + (o - 3) / 5;
+                    if (y + dy >= 0 && y + dy < ny && z + dz < nz) w += wt[o];
+                }
+                return w;
+            };
+            // y classes: 0, 1, interior, ny - 2, ny - 1;  z classes: interior, nz - 2, nz - 1
+            auto ycls = [&](int y) { return y < 2 ? y : (y >= ny - 2 ? 3 + (y - (ny - 2)) : 2); };
+            auto zcls = [&](int z) { return z >= nz - 2 ? 1 + (z - (nz - 2)) : 0; };
+            const int yrep[5] = {0, 1, 2, ny - 2, ny - 1}, zrep[3] = {0, nz - 2, nz - 1};
+            long long w[3][5], layer[3];
+            for (int a = 0; a < 3; ++a) {
+                for (int b = 0; b < 5; ++b) w[a][b] = wrow(yrep[b], zrep[a]);
+                layer[a] = w[a][0] + w[a][1] + (long long)(ny - 4) * w[a][2] + w[a][3] + w[a][4];
+            }
+            long long total = 0;
+            for (int z = 0; z < nz; ++z) total += layer[zcls(z)];
+            total *= g->nx;                                        // weight of a segment = row weight x its cells
+            auto boundary = [&](long long target) -> int {         // first segment at which the running weight reaches target
+                long long acc = 0;
+                for (int z = 0; z < nz; ++z) {
+                    const long long lw = layer[zcls(z)] * g->nx;
+                    if (acc + lw <= target && z + 1 < nz) { acc += lw; continue; }
+                    for (int y = 0; y < ny; ++y) {
+                        const long long rw = w[zcls(z)][ycls(y)];
+                        if (acc + rw * g->nx <= target && !(z + 1 == nz && y + 1 == ny)) { acc += rw * g->nx; continue; }
+                        for (int sx = 0; sx < g->nsx; ++sx) {
+                            const int cells = (sx + 1 == g->nsx) ? g->nx - sx * g->seg_len : g->seg_len;
+                            if (acc + rw * cells > target) return (z * ny + y) * g->nsx + sx;
+                            acc += rw * cells;
+                        }
+                        return (z * ny + y + 1) * g->nsx;
+                    }
+                }
+                return g->n_seg;
+            };
+            g->seg_lo = rank == 0 ? 0 : boundary(total * rank / world);
+            g->seg_hi = rank + 1 == world ? g->n_seg : boundary(total * (rank + 1) / world);
+        }
     }
     // FP32 candidate test on positions relative to the origin: coordinate error <= extent * 2^-24 each,
     // so |r_f - r| <= 4 * extent * 2^-23 with room to spare; r2 margin = 2 r dr + float product rounding
@@ -1033,7 +1085,7 @@ inline int run_cell_sort(CellPlan& p, const DeviceSystem& ds, cudaStream_t st, u
     const int scan_blocks = (a.max_cells + 1 + kScanBlock - 1) / kScanBlock;
     cudaMemsetAsync(a.work_ctr, 0, 8 * sizeof(int), st);          // work counters and flags
     bbox_kernel<<<a.bbox_blocks, 256, 0, st>>>(ds, a.bbox_part, a.flags);
-    grid_setup_kernel<<<1, 32, 0, st>>>(a.bbox_part, a.bbox_blocks, p.cutoff, a.max_cells, a.seg_target, a.grid);
+    grid_setup_kernel<<<1, 32, 0, st>>>(a.bbox_part, a.bbox_blocks, p.cutoff, a.max_cells, a.seg_target, a.rank, a.world, a.grid);
     zero_counts_kernel<<<std::min(592, (a.max_cells + 256) / 256), 256, 0, st>>>(a.grid, a.count, a.cursor);
     cell_assign_kernel<<<nb, 256, 0, st>>>(ds, a.grid, a.cell_of, a.count);
     scan_local_kernel<<<scan_blocks, kScanBlock, 0, st>>>(a.grid, a.count, a.start, a.block_sums, a.pad);

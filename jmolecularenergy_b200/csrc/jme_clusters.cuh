@@ -170,7 +170,7 @@ cl_list_kernel(CellArrays A, ClListArgs P) {
     const float4* __restrict__ fxyz = A.fxyz;
     const float qnan = __int_as_float(0x7fc00000);
 
-    const long long s0 = (long long)g.n_seg * P.rank / P.world, s1 = (long long)g.n_seg * (P.rank + 1) / P.world;
+    const long long s0 = g.seg_lo, s1 = g.seg_hi;
     const int cell0 = cl_seg_first_cell(g, s0), cell1 = cl_seg_first_cell(g, s1);
     const int n_items = (cell1 - cell0) * P.parts;
     for (;;) {
@@ -342,7 +342,7 @@ cl_mark_kernel(CellArrays A, const int* __restrict__ excl_src, uint2* __restrict
     const GridParams& g = *A.grid;
     {
         const int ci = A.scell[si];
-        const long long s0 = (long long)g.n_seg * rank / world, s1 = (long long)g.n_seg * (rank + 1) / world;
+        const long long s0 = g.seg_lo, s1 = g.seg_hi;
         if (ci < cl_seg_first_cell(g, s0) || ci >= cl_seg_first_cell(g, s1)) return;      // not this shard's list
     }
     const int q = si / C, a = si % C;
@@ -444,7 +444,7 @@ cl_pair_kernel(DeviceSystem S, CellArrays A, ClPairArgs P) {
     const GridParams g = *A.grid;
     const int H = g.n_half;
     const PosQ* __restrict__ spq = A.spq;
-    const long long s0 = (long long)g.n_seg * P.rank / P.world, s1 = (long long)g.n_seg * (P.rank + 1) / P.world;
+    const long long s0 = g.seg_lo, s1 = g.seg_hi;
     const unsigned int dummy_meta = (unsigned int)POOL | F::kAllExcl;        // lanes beyond the end of a list: slot POOL
     const size_t np = cl_pitch(A.start[g.ncell]);                // positions per slot array (xyz interleaved)
 
@@ -792,7 +792,7 @@ struct ClReduceArgs {
 __global__ void __launch_bounds__(256)
 cl_cellmask_kernel(CellArrays A, int rank, int world, uint2* __restrict__ mask) {
     const GridParams& g = *A.grid;
-    const long long s0 = (long long)g.n_seg * rank / world, s1 = (long long)g.n_seg * (rank + 1) / world;
+    const long long s0 = g.seg_lo, s1 = g.seg_hi;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < g.ncell; c += gridDim.x * blockDim.x) {
         if (A.count[c] == 0) { mask[c] = make_uint2(0u, 0u); continue; }
         const int cx = c % g.nx, cy = (c / g.nx) % g.ny, cz = c / (g.nx * g.ny);
@@ -827,7 +827,7 @@ cl_reduce_kernel(CellArrays A, ClReduceArgs Q) {
     const GridParams& g = *A.grid;
     if (blockIdx.x == gridDim.x - 1) {
         // last block: energies and pair counts over this shard's segments
-        const long long s0 = (long long)g.n_seg * Q.rank / Q.world, s1 = (long long)g.n_seg * (Q.rank + 1) / Q.world;
+        const long long s0 = g.seg_lo, s1 = g.seg_hi;
         ReduceArgs R = Q.R;
         R.epart += 2 * s0; R.cpart += 2 * s0; R.n_epart = (int)(s1 - s0);
         R.overflow = A.flags;
