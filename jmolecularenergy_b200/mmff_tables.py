@@ -137,6 +137,22 @@ class MMFFTables:
             for r in _rows(p("MMFF94-bond-charge-increment.par"))]
         self.pbci: List[Tuple[np.float32, np.float32]] = [
             (f32(r[1]), f32(r[2])) for r in _rows(p("MMFF94-partial-charge-increment.par"))]
+        # indices for the full assignment port (assign.py): first row wins, like the reference's linear scans
+        self.bci_by_key: Dict[Tuple[int, int, int], np.float32] = {}
+        for row in self.bci:
+            self.bci_by_key.setdefault((row[0], row[1], row[2]), row[3])
+        self.angle_by_centre: Dict[int, List[tuple]] = {}
+        for row in self.angle:
+            self.angle_by_centre.setdefault(row[2], []).append(row)
+        self.torsion_by_centre: Dict[Tuple[int, int], List[tuple]] = {}
+        for row in self.torsion:
+            self.torsion_by_centre.setdefault((row[2], row[3]), []).append(row)
+        # (atomic number 1 <= atomic number 2) -> (kb, r0) of the default-rule bond table (MMFF94Parameters.java:236-248)
+        self.bond_empirical: Dict[Tuple[int, int], Tuple[np.float32, np.float32]] = {}
+        emp_b = p("MMFF94-bond-stretch-empirical.par")
+        if os.path.exists(emp_b):
+            for r in _rows(emp_b):
+                self.bond_empirical.setdefault((int(r[0]), int(r[1])), (f32(r[3]), f32(r[2])))
 
     # ---- per-type rows -------------------------------------------------
     def vdw_row(self, t: int) -> VdwRow:

@@ -1,0 +1,56 @@
+"""Host-side parameter assignment port (jmolecularenergy_b200/assign.py): ring perception,
+the table lookups and the empirical rules.  The `.par` tables are the reference's (not shipped): the checks that need
+them run where /root/reference exists (the build container) and are skipped elsewhere.  The real proof of this module
+is tests/golden: 317 molecules of the reference's two validation suites, typed by rule, parameterised by this code,
+reproduce their published energies and charges (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from jmolecularenergy_b200.assign import Assigner, assign_parameters, find_rings
+
+PAR_DIR = "/root/reference/src/main/resources/org/jme/forcefield/mmff"
+needs_tables = pytest.mark.skipif(not os.path.isdir(PAR_DIR), reason="the reference's .par tables are not on this machine")
+
+
+def test_find_rings_counts():
+    hexagon = [(k, (k + 1) % 6) for k in range(6)]
+    assert [len(r) for r in find_rings(6, hexagon)] == [6]
+    # naphthalene skeleton: two fused six-rings sharing the bond 0-5, and the ten-membered envelope
+    naph = hexagon + [(0, 6), (6, 7), (7, 8), (8, 9), (9, 5)]
+    assert sorted(len(r) for r in find_rings(10, naph, max_size=10)) == [6, 6, 10]
+    # bicyclo[1.1.0]butane: two three-rings and the four-ring around them
+    assert sorted(len(r) for r in find_rings(4, [(0, 1), (1, 2), (2, 0), (1, 3), (3, 2)])) == [3, 3, 4]
+    assert find_rings(5, [(0, 1), (1, 2), (2, 3), (3, 4)]) == []
+
+
+@needs_tables
+def test_ethanol_reassigned_equals_the_fixture():
+    from jmolecularenergy_b200.mmff_tables import MMFFTables
+    s = load_golden("ETHANOL")
+    bonds = list(zip(s.bond_i.tolist(), s.bond_j.tolist()))
+    t = assign_parameters(MMFFTables(PAR_DIR), s.xyz, s.atom_type.tolist(), bonds, [1] * len(bonds))
+    for k in ("charge", "bond_kb", "bond_r0", "angle_ka", "angle_theta0", "stbn_kba_ijk", "stbn_kba_kji", "tor_v1", "tor_v2", "tor_v3"):
+        np.testing.assert_array_equal(getattr(t, k), getattr(s, k), err_msg=k)
+
+
+@needs_tables
+def test_ring_angle_and_torsion_types():
+    from jmolecularenergy_b200.mmff_tables import MMFFTables
+    tables = MMFFTables(PAR_DIR)
+    # cyclobutane carbons (CR4R = 20) with two hydrogens each: ring angles are type 4, ring torsions type 4
+    bonds = [(0, 1), (1, 2), (2, 3), (3, 0)] + [(c, 4 + 2 * c + h) for c in range(4) for h in range(2)]
+    a = Assigner(tables, [20] * 4 + [5] * 8, bonds, [1] * len(bonds))
+    assert a.angle_type(0, 1, 2) == 4 and a.angle_type(4, 0, 1) == 0
+    for x, y in bonds:
+        a.r0[(x, y)] = a.r0[(y, x)] = a.bond_parameters(x, y)[1]
+    ka, th0 = a.angle_parameters(0, 1, 2)
+    assert 80.0 < float(th0) < 95.0 and float(ka) > 0
+    v = a.torsion_parameters(0, 1, 2, 3)
+    assert len(v) == 3
+    # cyclopropane (CR3R = 22): angle type 3
+    bonds3 = [(0, 1), (1, 2), (2, 0)] + [(c, 3 + 2 * c + h) for c in range(3) for h in range(2)]
+    b = Assigner(tables, [22] * 3 + [5] * 6, bonds3, [1] * len(bonds3))
+    assert b.angle_type(0, 1, 2) == 3
