@@ -49,6 +49,7 @@ PAR_DIR = f"{REF}/src/main/resources/org/jme/forcefield/mmff"
 MOL2 = f"{REF}/src/test/resources/org/jme/forcefield/mmff/MMFF94_dative.mol2"
 ENERGIES = f"{REF}/src/test/resources/org/jme/forcefield/mmff/MMFF94.energies"
 
+LAST_AROMATIC_BONDS = set()
 WATER = {"O": 70, "H": 31}
 # name -> (type per atom by mol2 atom order | callable(symbol)->type, {atom index: formal charge})
 HAND_TYPED = {
@@ -121,11 +122,52 @@ def auto_types(atoms, bonds, allow_rings=False):
         for a in r:
             ring_sizes[a].add(len(r))
     arom_bonds = {frozenset((a, b)) for a, b, o in bonds if o == "ar"}
-    for r in rings:                           # aromatic systems other than six-membered rings are left alone
+    for r in rings:                           # mol2 "ar" systems other than six-membered rings are left alone
         ar_in_ring = sum(1 for k in range(len(r)) if frozenset((r[k], r[(k + 1) % len(r)])) in arom_bonds)
-        if ar_in_ring and (len(r) != 6 or ar_in_ring != 6) and len(r) <= 7:
-            if ar_in_ring == len(r):
-                return None
+        if ar_in_ring == len(r) and len(r) != 6:
+            return None
+    # Aromaticity from the Kekule structure (the suites write rings with alternating single / double bonds):
+    #  * six-membered rings of C / N in which every atom has a double bond inside the ring or already belongs to an
+    #    aromatic ring (fused benzenoids), iterated to a fixed point;
+    #  * five-membered rings with two ring double bonds and exactly one atom that donates a lone pair (O, S, or N with
+    #    three neighbours): furans, thiophenes, pyrroles, azoles.
+    order_of = {frozenset((a, b)): ("2" if o == "ar" else ("1" if o == "am" else o)) for a, b, o in bonds}
+    ring_bonds = lambda r: [frozenset((r[k], r[(k + 1) % len(r)])) for k in range(len(r))]
+    arom_ring = []
+    changed = True
+    while changed:
+        changed = False
+        for r in rings:
+            if r in arom_ring or len(r) != 6 or any(el[a] not in ("C", "N") for a in r):
+                continue
+            rb = ring_bonds(r)
+            ok = all(any(order_of[b] == "2" and a in b for b in rb) or aromatic_atom[a] for a in r)
+            if ok and all(len(nb[a]) <= 3 for a in r):
+                arom_ring.append(r)
+                for a in r:
+                    aromatic_atom[a] = True
+                arom_bonds.update(rb)
+                changed = True
+    five_role = {}                            # atom -> "X" (lone-pair donor), "A" (alpha to it), "B" (beta)
+    for r in rings:
+        if len(r) != 5:
+            continue
+        rb = ring_bonds(r)
+        donors = [a for a in r if (el[a] in ("O", "S") and len(nb[a]) == 2) or (el[a] == "N" and len(nb[a]) == 3
+                                                                                and all(o == 1 for _, o in nb[a]))]
+        n_dbl = sum(1 for b in rb if order_of[b] == "2")
+        others_sp2 = all(any(o == 2 for _, o in nb[a]) or aromatic_atom[a] for a in r if a not in donors)
+        if len(donors) == 1 and others_sp2 and (n_dbl == 2 or (n_dbl == 1 and any(aromatic_atom[a] for a in r))) \
+                and all(el[a] in ("C", "N", "O", "S") for a in r):
+            x = r.index(donors[0])
+            five_role[r[x]] = "X"
+            for d, role in ((1, "A"), (4, "A"), (2, "B"), (3, "B")):
+                five_role.setdefault(r[(x + d) % 5], role)
+            arom_bonds.update(rb)
+            for a in r:
+                aromatic_atom[a] = True
+    global LAST_AROMATIC_BONDS
+    LAST_AROMATIC_BONDS = arom_bonds
 
     def double_to(i, els):
         return any(o == 2 and el[j] in els for j, o in nb[i])
@@ -139,7 +181,10 @@ def auto_types(atoms, bonds, allow_rings=False):
         if e == "C":
             if deg == 4:
                 t[i] = 22 if 3 in ring_sizes[i] else (20 if 4 in ring_sizes[i] else 1)     # CR3R, CR4R, CR
-            elif deg == 3 and aromatic_atom[i]:
+            elif deg == 3 and five_role.get(i) in ("A", "B") and not double_to(i, ("O", "S")) \
+                    and not any(o == 2 and not aromatic_atom[j] for j, o in nb[i]):
+                t[i] = 63 if five_role[i] == "A" else 64                                   # C5A, C5B
+            elif deg == 3 and aromatic_atom[i] and not any(o == 2 and not aromatic_atom[j] for j, o in nb[i]):
                 t[i] = 37                                                                  # CB
             elif deg == 3 and mo == 2:
                 if double_to(i, ("O", "N", "S")):
@@ -153,7 +198,9 @@ def auto_types(atoms, bonds, allow_rings=False):
             else:
                 return None
         elif e == "O":
-            if deg == 2:
+            if deg == 2 and five_role.get(i) == "X":
+                t[i] = 59                                                                  # OFUR
+            elif deg == 2:
                 t[i] = 70 if all(el[j] == "H" for j, _ in nb[i]) else 6
             elif deg == 1:
                 j, o = nb[i][0]
@@ -172,6 +219,8 @@ def auto_types(atoms, bonds, allow_rings=False):
                 return None
         elif e == "S":
             t[i] = {(2, 1): 15, (1, 2): 16}.get((deg, mo), {3: 17, 4: 18}.get(deg, 0))
+            if deg == 2 and five_role.get(i) == "X":
+                t[i] = 44                                                                  # STHI
             if not t[i]:
                 return None
         elif e == "P":
@@ -191,6 +240,12 @@ def auto_types(atoms, bonds, allow_rings=False):
             continue
         deg, mo = len(nb[i]), top(i)
         if aromatic_atom[i]:
+            if five_role.get(i) == "X" and deg == 3:
+                t[i] = 39                                                                  # NPYL
+                continue
+            if five_role.get(i) in ("A", "B") and deg == 2:
+                t[i] = 65 if five_role[i] == "A" else 66                                   # N5A, N5B
+                continue
             if deg == 2:
                 t[i] = 38                                                                  # NPYD
                 continue
@@ -226,7 +281,7 @@ def auto_types(atoms, bonds, allow_rings=False):
         elif e in ("S", "P"):
             t[i] = 71
         elif e == "N":
-            t[i] = {8: 23, 10: 28, 40: 28, 43: 28, 9: 27}.get(t[j], 0)
+            t[i] = {8: 23, 10: 28, 40: 28, 43: 28, 9: 27, 39: 23}.get(t[j], 0)
         elif e == "O":
             if t[j] == 70:
                 t[i] = 31
@@ -235,7 +290,7 @@ def auto_types(atoms, bonds, allow_rings=False):
                 if len(x) == 1:
                     x = x[0]
                     if el[x] == "C":
-                        t[i] = 24 if double_to(x, ("O",)) else (29 if t[x] in (2, 3, 37, 30) else 21)
+                        t[i] = 24 if double_to(x, ("O",)) else (29 if t[x] in (2, 3, 37, 30, 63, 64) else 21)
                     elif el[x] == "S":
                         t[i] = 33
                     elif el[x] == "P":
@@ -464,6 +519,9 @@ def pin_suite(tables, mol2_path, energies_path, prefix, hand_typed, kept, tolera
         xyz = [[a[1], a[2], a[3]] for a in m["atoms"]]
         bonds = [(a, b) for a, b, _ in m["bonds"]]
         aromatic = [o == "ar" for _, _, o in m["bonds"]]
+        if how.startswith("rule"):               # the perception of auto_types (run again: it keeps the last result)
+            auto_types(m["atoms"], m["bonds"], allow_rings=True)
+            aromatic = [frozenset((a, b)) in LAST_AROMATIC_BONDS for a, b, _ in m["bonds"]]
         expected, eline = energies[name]
         src = (f"{os.path.basename(mol2_path)}:{m['line']} / {os.path.basename(energies_path)}:{eline} (OPTIMOL); "
                f"{how} types {types}")
