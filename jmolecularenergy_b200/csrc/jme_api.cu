@@ -347,7 +347,7 @@ int ensure_plan(jme_handle* h) {
     } else {
         // the two evaluation schemes of the cutoff path: cluster lists (4 atoms per cluster) for large systems,
         // per-atom lists below; JME_PATH_CELLS_LISTS / _CLUSTERS force one, JME_CLUSTER (0, 2, 4) is a development knob
-        int cluster = h->hs.n >= kClusterPathMinAtoms ? 4 : 0;
+        int cluster = h->hs.n / std::max(1, h->world) >= kClusterPathMinAtoms ? 4 : 0;       // atoms per rank
         if (h->path == JME_PATH_CELLS_LISTS) cluster = 0;
         if (h->path == JME_PATH_CELLS_CLUSTERS) cluster = 4;
         if (const char* e = std::getenv("JME_CLUSTER")) {

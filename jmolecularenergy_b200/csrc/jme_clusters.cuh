@@ -934,8 +934,10 @@ inline int cl_configure(CellPlan& p, const DeviceSystem& ds, std::string& err) {
     p.cl_warps = kClWarps;
     p.cl_smem_grad = tb + kClWarps * cl_warp_smem(true, (int)pool);
     p.cl_smem_energy = tb + kClWarps * cl_warp_smem(false, (int)pool);
-    // about four segments per resident warp
-    p.arr.seg_target = 4 * p.sms * kClWarps;
+    // about four segments per resident warp of THIS rank's shard (the shards of a multi-GPU job are 1 / world of the
+    // segments each: with the single-GPU segment length a rank at N = 4 had 1.6 segments per warp and its pair
+    // kernel ran 45 % over its share)
+    p.arr.seg_target = 4 * p.sms * kClWarps * std::max(1, p.world);
     return JME_OK;
 }
 
