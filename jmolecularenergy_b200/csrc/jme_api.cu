@@ -576,7 +576,8 @@ int grow_cell_lists(jme_handle* h, int what = 1) {
     CellPlan& p = h->cells;
     int cap = p.list_cap, ccap = p.cluster_cap;
     if (what & 1) cap *= 2;
-    if (cap > (1 << 16)) { h->err = "survivor-list capacity limit"; return JME_ERR_NOMEM; }
+    // (cluster lists: a list is at most kClTripTab trips of the FP64 kernel)
+    if (cap > (p.cluster != 0 ? 4096 : (1 << 16))) { h->err = "survivor-list capacity limit"; return JME_ERR_NOMEM; }
     int rc;
     if (p.cluster != 0) {
         if (what & 2) ccap = std::min(std::max(1, h->ds.n), std::max(ccap + 1, ccap * 2));

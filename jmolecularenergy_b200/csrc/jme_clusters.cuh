@@ -136,6 +136,7 @@ struct ClListArgs {
     int parts;                     // warps sharing one cell (small systems)
     int rank, world;
     const unsigned int* layout;    // [segments][16] ring of every half-shell row in the sweeping warp's window (cl_layout_kernel)
+    int pool;                      // the dummy window slot (padding entries)
 };
 
 // if (pred) base[index] = v (8 bytes), as a predicated streaming store with a single-instruction address
@@ -237,6 +238,7 @@ cl_list_kernel(CellArrays A, ClListArgs P) {
                 fis[lane][2] = make_float2(f.z, f.z);
             }
             int my_cnt = 0;                                           // lane kq holds the list length of cluster ch / C + kq
+            bool beyond = false;                                      // a candidate of this lane lies beyond the ring of its row
             __syncwarp();
             unsigned long long rows = reinterpret_cast<unsigned long long>(P.list + (size_t)(ch / C) * P.cap);
             asm volatile("" : "+l"(rows));                            // keep the base in registers
@@ -261,8 +263,9 @@ cl_list_kernel(CellArrays A, ClListArgs P) {
                     // origin of its row; a partner further from the window start than the ring is long is flagged
                     const int4 rg = rings[r[k]];
                     const int slot = rg.x + (rg.y > 0 ? cl_ring_mod(valid ? j - p0s[r[k]] : 0, rg.y, (unsigned int)rg.z) : 0);
-                    meta[k] = (unsigned int)slot | ((unsigned int)__float_as_int(a.w) << kMetaTypeShift) |
-                              (j - cws[r[k]] >= rg.y ? kMetaOvf : 0u);
+                    const bool ovf = valid && j - cws[r[k]] >= rg.y;
+                    beyond = beyond || ovf;
+                    meta[k] = (unsigned int)slot | ((unsigned int)__float_as_int(a.w) << kMetaTypeShift) | (ovf ? kMetaOvf : 0u);
                 }
                 unsigned long long px[kListK / 2], py[kListK / 2], pz[kListK / 2];
 #pragma unroll
@@ -318,7 +321,18 @@ cl_list_kernel(CellArrays A, ClListArgs P) {
                     }
                 }
             }
-            if (lane < nq) P.count[ch / C + lane] = my_cnt;
+            // every list is padded to whole trips (at least one) with dummy entries - the cluster's own first atom,
+            // every pair excluded, the dummy window slot - so that the FP64 kernel loads entries unconditionally; bit 30
+            // of the count: some candidate of this cell lies beyond its ring, the clusters' trips need the atomics
+            const bool cell_ovf = __any_sync(0xffffffffu, beyond);
+            for (int kq = 0; kq < nq; ++kq) {
+                const int cnt = __shfl_sync(0xffffffffu, my_cnt, kq);
+                const int full = min(P.cap, max(F::kSpan, (cnt + F::kSpan - 1) / F::kSpan * F::kSpan));
+                for (int i = cnt + lane; i < full; i += 32)
+                    st_cs_if64(true, rows, (unsigned int)(kq * P.cap + i),
+                               make_uint2((unsigned int)(ch + C * kq), (unsigned int)P.pool | F::kAllExcl));
+            }
+            if (lane < nq) P.count[ch / C + lane] = my_cnt | (cell_ovf ? 0x40000000 : 0);
         }
     }
     (void)F::kK;
@@ -348,7 +362,7 @@ cl_mark_kernel(CellArrays A, const int* __restrict__ excl_src, uint2* __restrict
     const int q = si / C, a = si % C;
     if (q >= ccap) return;
     uint2* lst = list + (size_t)q * cap;
-    const int n = min(count[q], cap);
+    const int n = min(count[q] & 0x3fffffff, cap);
     int lo = 0, hi = n;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
@@ -397,13 +411,15 @@ __device__ __forceinline__ void warp_multi_sum(double (&v)[N], int lane) {
     for (; m > 0; m >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], m);
 }
 
-// per-warp shared memory: the force window (3 planes of kClMaxRows * ring + 8 doubles: the extra ones hold the dummy
-// slot of lanes beyond the end of a list), the row table and the batch's cluster data
+// per-warp shared memory: the force window (3 planes of pool + 8 doubles: the extra ones hold the dummy slot of the
+// padding entries), the row table (window start of every half-shell row for every cell of the segment + the final
+// frontier), the row constants, the batch's cluster data, the trip table and the parked cluster atoms
 __host__ __device__ constexpr size_t cl_window_plane(int pool) { return (size_t)pool + 8; }
 constexpr int kClNextBytes = 2 * (4 * 32 + 16);   // the current and the next cluster's atoms (C records + C types), ping-pong
+constexpr int kClTripTab = 254;                   // trips of a batch; two more descriptors pad the table (the look-ahead of the pipeline)
 __host__ __device__ constexpr size_t cl_warp_smem(bool grad, int pool) {
-    return (grad ? 3 * cl_window_plane(pool) * sizeof(double) : 0) + kClMaxSegLen * kClRowPitch * sizeof(int) +
-           2 * kClBatch * sizeof(int) + kClNextBytes;
+    return (grad ? 3 * cl_window_plane(pool) * sizeof(double) : 0) + (kClMaxSegLen + 1) * kClRowPitch * sizeof(int) +
+           kClRowPitch * sizeof(int4) + 2 * kClBatch * sizeof(int) + kClNextBytes + (kClTripTab + 2) * sizeof(unsigned short);
 }
 
 __device__ __forceinline__ uint2 ld_entry(const uint2* p) {
@@ -414,6 +430,13 @@ __device__ __forceinline__ uint2 ld_entry(const uint2* p) {
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // TSM: the type-pair table sits in shared memory (LDS.128); otherwise it is read through L1 / L2
+//
+// Structure of a sweep: segment -> batches of <= 32 clusters -> clusters -> trips.  The trips of a batch are numbered
+// through (trip table: list offset of every trip), so the software pipeline - entries two trips ahead, partner records
+// one trip ahead - runs across cluster boundaries, and the trip loop of a cluster is ONE basic block: every list is
+// padded to whole trips by the list kernel (dummy entries: everything excluded, dummy window slot), every load is
+// unconditional, the window update of a trip is carried into the next one.  Clusters whose list holds a partner
+// beyond its ring (count bit 30) run a second instance of the loop that has the atomics.
 template <int C, bool GRAD, bool EMIT, bool TSM>
 __global__ void __launch_bounds__(32 * kClWarps, 1)
 cl_pair_kernel(DeviceSystem S, CellArrays A, ClPairArgs P) {
@@ -429,10 +452,12 @@ cl_pair_kernel(DeviceSystem S, CellArrays A, ClPairArgs P) {
     unsigned char* wbase = smem_raw + (TSM ? (((size_t)TT * sizeof(PairConst) + 15) & ~(size_t)15) : 0) +
                            (size_t)warp * cl_warp_smem(GRAD, POOL);
     double* acc = reinterpret_cast<double*>(wbase);                                      // [3][plane] (GRAD)
-    int* rowtab = reinterpret_cast<int*>(wbase + (GRAD ? 3 * (size_t)plane * sizeof(double) : 0));   // [cell of the segment][row]: window start
-    int* s_cnt = rowtab + kClMaxSegLen * kClRowPitch;                                    // list length of the batch's clusters
+    int4* rowc = reinterpret_cast<int4*>(wbase + (GRAD ? 3 * (size_t)plane * sizeof(double) : 0));   // row o: {ring origin, first slot, slots, floor(2^32 / slots)}
+    int* rowtab = reinterpret_cast<int*>(rowc + kClRowPitch);                            // [cell of the segment (+ the end)][row]: window start
+    int* s_cnt = rowtab + (kClMaxSegLen + 1) * kClRowPitch;                              // list length of the batch's clusters (bit 30: needs the atomics)
     int* s_ci = s_cnt + kClBatch;                                                        // their cell (index inside the segment)
     uint4* s_next = reinterpret_cast<uint4*>(s_ci + kClBatch);                           // the next cluster's C records, then its C types
+    unsigned short* s_trip = reinterpret_cast<unsigned short*>(reinterpret_cast<unsigned char*>(s_next) + kClNextBytes);
     if (TSM) {
         for (int t = threadIdx.x; t < TT; t += blockDim.x) s_table[t] = S.table[t];
     }
@@ -445,8 +470,8 @@ cl_pair_kernel(DeviceSystem S, CellArrays A, ClPairArgs P) {
     const int H = g.n_half;
     const PosQ* __restrict__ spq = A.spq;
     const long long s0 = g.seg_lo, s1 = g.seg_hi;
-    const unsigned int dummy_meta = (unsigned int)POOL | F::kAllExcl;        // lanes beyond the end of a list: slot POOL
     const size_t np = cl_pitch(A.start[g.ncell]);                // positions per slot array (xyz interleaved)
+    const int tpc = P.cap / F::kSpan;                            // trips a list can hold (the cap is a multiple of 64)
 
     for (;;) {
         long long seg = 0;
@@ -457,57 +482,56 @@ cl_pair_kernel(DeviceSystem S, CellArrays A, ClPairArgs P) {
         const int xa = sx * g.seg_len, xb = min(xa + g.seg_len, g.nx);
         const int cy = row % g.ny, cz = row / g.ny;
         const int rowbase = row * g.nx;
-        const int q0 = A.start[rowbase + xa] / C, q1 = A.start[rowbase + xb] / C;      // the segment's clusters
+        const int q0 = A.start[rowbase + xa] / C;
+        const int q1 = min(A.start[rowbase + xb] / C, P.ccap);   // the segment's clusters (beyond the list storage: flags[3], the host retries)
         double ev = 0, ee = 0;
         unsigned long long n_cand_w = 0;
         unsigned int n_eval = 0;
         if (q0 < q1) {
-            // lane o < H looks after half-shell row o: its cell row, the ring origin (sorted position of ring slot 0)
-            // and the flush frontier (first position not yet written to the slot array)
-            int my_rowbase = -1, my_p0 = 0, my_lo = 0, my_base = 0, my_cap = 0;
-            unsigned int my_magic = 0;
-            if (lane < 16) {
-                const unsigned int lay = P.layout[seg * 16 + lane];
-                my_base = (int)(lay & 0xffffu);
-                my_cap = (int)(lay >> 16);
-                my_magic = my_cap > 0 ? (unsigned int)(0x100000000ull / (unsigned long long)my_cap) : 0u;
-            }
-            if (lane < H) {
-                int dy, dz;
-                cl_row_offset(lane, g.reach, dy, dz);
-                const int y2 = cy + dy, z2 = cz + dz;
-                if (y2 >= 0 && y2 < g.ny && z2 < g.nz) {
-                    my_rowbase = (z2 * g.ny + y2) * g.nx;
-                    my_p0 = my_lo = A.start[my_rowbase + max(xa - g.reach, 0)];
+            {   // lane o < H looks after half-shell row o: the ring of the row and where its window starts for every
+                // cell of the segment (the last line: where it ends when the sweep is over)
+                int rb = -1;
+                if (lane < H) {
+                    int dy, dz;
+                    cl_row_offset(lane, g.reach, dy, dz);
+                    const int y2 = cy + dy, z2 = cz + dz;
+                    if (y2 >= 0 && y2 < g.ny && z2 < g.nz) rb = (z2 * g.ny + y2) * g.nx;
                 }
+                __syncwarp();
+                if (lane < kClRowPitch) {
+                    const unsigned int lay = P.layout[seg * 16 + lane];
+                    const int cap = (int)(lay >> 16);
+                    rowc[lane] = make_int4(rb >= 0 ? A.start[rb + max(xa - g.reach, 0)] : 0, (int)(lay & 0xffffu), cap,
+                                           cap > 0 ? (int)(0x100000000ull / (unsigned long long)cap) : 0);
+                }
+                const int nc = xb - xa;
+                for (int ci = 0; ci <= nc; ++ci) {
+                    int v = 0;
+                    if (rb >= 0) v = ci < nc ? A.start[rb + max(xa + ci - g.reach, 0)] : A.start[rb + min(xb - 1 + g.reach, g.nx - 1) + 1];
+                    if (lane < kClRowPitch) rowtab[ci * kClRowPitch + lane] = v;
+                }
+                __syncwarp();
             }
-            __syncwarp();
-            for (int ci = 0; ci < xb - xa; ++ci) {
-                int v = 0;
-                if (my_rowbase >= 0) v = A.start[my_rowbase + max(xa + ci - g.reach, 0)];
-                if (lane < kClRowPitch) rowtab[ci * kClRowPitch + lane] = v;
-            }
-            __syncwarp();
             const int slot_par = sx & 1;
-            // flush the window rows up to the given frontier (per row: `target`, held by lane o)
-            auto flush_to = [&](int target) {
-                for (int o = 0; o < (GRAD ? H : 0); ++o) {
-                    const int rb = __shfl_sync(FULL, my_rowbase, o);
-                    const int lo = __shfl_sync(FULL, my_lo, o);
-                    const int hi = __shfl_sync(FULL, target, o);
-                    const int p0 = __shfl_sync(FULL, my_p0, o);
-                    const int base = __shfl_sync(FULL, my_base, o), cap = __shfl_sync(FULL, my_cap, o);
-                    const unsigned int magic = __shfl_sync(FULL, my_magic, o);
-                    if (rb < 0 || hi <= lo) continue;
+            // flush the window rows from the frontier of cell `from` to that of cell `to`: two rows at a time, 16 lanes
+            // each; positions beyond a row's ring were never accumulated here (they went through the atomics): zeros
+            auto flush = [&](int from, int to) {
+                if constexpr (GRAD) {
+#pragma unroll 1
+                for (int o2 = 0; o2 < H; o2 += 2) {
+                    const int o = o2 + (lane >> 4);
+                    const int lo = rowtab[from * kClRowPitch + o], hi = rowtab[to * kClRowPitch + o];   // (row 13..15: zeros)
+                    const int4 rc = rowc[o];
+                    const int n = o < H ? hi - lo : 0;
+                    if (n <= 0) continue;
                     double* dst = P.gj + ((size_t)(2 * o + slot_par) * np + lo) * 3;
-                    const int r0 = cap > 0 ? cl_ring_mod(lo - p0, cap, magic) : 0;
-                    for (int d = lane; d < hi - lo; d += 32) {
-                        const bool in_ring = d < cap;                 // positions beyond the ring were never accumulated here
+                    const int r0 = rc.z > 0 ? cl_ring_mod(lo - rc.x, rc.z, (unsigned int)rc.w) : 0;
+                    for (int d = lane & 15; d < n; d += 16) {
                         int ri = r0 + d;
-                        if (ri >= cap) ri -= cap;
-                        const int idx = base + ri;
+                        if (ri >= rc.z) ri -= rc.z;
+                        const int idx = rc.y + ri;
                         double vx = 0, vy = 0, vz = 0;
-                        if (in_ring) {
+                        if (d < rc.z) {
                             vx = acc[idx]; vy = acc[plane + idx]; vz = acc[2 * plane + idx];
                             acc[idx] = 0.0; acc[plane + idx] = 0.0; acc[2 * plane + idx] = 0.0;
                         }
@@ -515,48 +539,49 @@ cl_pair_kernel(DeviceSystem S, CellArrays A, ClPairArgs P) {
                         dst[3 * d + 1] = vy;
                         dst[3 * d + 2] = vz;
                     }
-                    if (lane == o) my_lo = hi;
                 }
                 __syncwarp();
+                }
             };
             int cur_ci = 0;                                       // the windows stand at the segment's first cell
 
-            for (int qb = q0; qb < q1; qb += kClBatch) {
-                const int nq = min(kClBatch, q1 - qb);
-                __syncwarp();                                     // the previous batch's reads of s_cnt / s_ci are over
-                s_cnt[lane] = lane < nq && qb + lane < P.ccap ? min(P.count[qb + lane], P.cap) : 0;
-                s_ci[lane] = lane < nq ? A.scell[C * (qb + lane)] - rowbase - xa : 0;
+            for (int qb = q0; qb < q1;) {
+                __syncwarp();                                     // the previous batch's reads of the tables are over
+                int nq, ntrip;
+                {   // the batch: up to 32 clusters, fewer if their trips do not fit the table
+                    const int q = qb + lane;
+                    const int raw = q < q1 ? P.count[q] : 0;
+                    const int cnt = min(raw & 0x3fffffff, P.cap);
+                    int T = q < q1 ? min(max(1, (cnt + F::kSpan - 1) / F::kSpan), kClTripTab) : 0;
+                    int incl = T;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(FULL, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    nq = __popc(__ballot_sync(FULL, q < q1 && incl <= kClTripTab));      // (>= 1: a list has at most kClTripTab trips)
+                    ntrip = __shfl_sync(FULL, incl, nq - 1);
+                    s_cnt[lane] = cnt | (raw & 0x40000000);
+                    s_ci[lane] = q < q1 ? A.scell[C * q] - rowbase - xa : 0;
+                    if (lane < nq) {
+                        for (int t = 0; t < T; ++t) s_trip[incl - T + t] = (unsigned short)(lane * tpc + t);
+                    }
+                    if (lane < 2) s_trip[ntrip + lane] = 0;       // look-ahead beyond the batch: its first trip again (never evaluated)
+                }
                 __syncwarp();
                 {   // the batch's first two lists on their way to L2
-                    const int n0 = s_cnt[0], n1 = nq > 1 ? s_cnt[1] : 0;
+                    const int n0 = s_cnt[0] & 0x3fffffff, n1 = nq > 1 ? s_cnt[1] & 0x3fffffff : 0;
                     if (16 * lane < n0) prefetch_l2(P.list + (size_t)qb * P.cap + 16 * lane);
                     if (16 * lane < n1) prefetch_l2(P.list + (size_t)(qb + 1) * P.cap + 16 * lane);
                 }
-                // the stream of trips: (cluster, trip) of the trip being evaluated and of the two behind it in the
-                // software pipeline; every cluster has at least one trip (an empty list still writes its i-side zeros)
-                auto trips_of = [&](int il) { return max(1, (s_cnt[il] + F::kSpan - 1) / F::kSpan); };
-                auto load_entries = [&](int il, int t, uint2 (&E)[K]) {
-                    const uint2* src = P.list + (size_t)(qb + il) * P.cap + F::kSpan * t + lane;
-                    const int n = s_cnt[il];
+                const uint2* lbase = P.list + (size_t)qb * P.cap + lane;
+                auto load_entries = [&](int k, uint2 (&E)[K]) {   // trip k of the batch
+                    const uint2* src = lbase + (size_t)s_trip[k] * F::kSpan;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        E[k] = make_uint2((unsigned int)(C * (qb + il)), dummy_meta);
-                        if (F::kSpan * t + 32 * k + lane < n) E[k] = ld_entry(src + 32 * k);
-                    }
+                    for (int kk = 0; kk < K; ++kk) E[kk] = ld_entry(src + 32 * kk);
                 };
-                int il = 0, t = 0, T = trips_of(0);               // being evaluated
-                int il1 = 0, t1 = 0, T1 = T;                      // next trip (its records are gathered now)
-                int il2, t2, T2;                                  // the trip after it (its entries are loaded now)
-                auto advance = [&](int& i, int& tt, int& TT_) {
-                    if (tt + 1 < TT_) { ++tt; return; }
-                    ++i; tt = 0;
-                    TT_ = i < nq ? trips_of(i) : 1;
-                };
-                advance(il1, t1, T1);
-                il2 = il1; t2 = t1; T2 = T1;
-                advance(il2, t2, T2);
 
-                int ci = 0, ipos0 = 0;
+                int ipos0 = 0;
                 double qi2[C], gix[C], giy[C], giz[C];
                 unsigned int trow[C];                             // byte offset of the atom's row of the type-pair table
                 unsigned int pad_excl = 0;                        // "excluded" bits of the cluster's padding atoms
@@ -575,112 +600,76 @@ cl_pair_kernel(DeviceSystem S, CellArrays A, ClPairArgs P) {
                     else if (lane < 2 * C + C) reinterpret_cast<unsigned int*>(dst + 2 * C)[lane - 2 * C] = v.x;
                 };
                 uint4 nxt = fetch_cluster(qb);
-                bool nxt_pending = false;
                 __syncwarp();
                 park_cluster(nxt);
                 __syncwarp();
                 const double* cp = reinterpret_cast<const double*>(s_next);      // x, y, z, q of the cluster's atoms
-#pragma unroll
-                for (int a = 0; a < C; ++a) {
-                    qi2[a] = gix[a] = giy[a] = giz[a] = 0.0;
-                    trow[a] = 0;
-                }
                 uint2 E0[K], E1[K];
-                PosQ G[K], Gn[K];
-                load_entries(0, 0, E0);
-                if (il1 < nq) load_entries(il1, t1, E1);
+                PosQ G[K];
+                load_entries(0, E0);
+                load_entries(1, E1);
 #pragma unroll
-                for (int k = 0; k < K; ++k) { G[k] = load_posq(spq + E0[k].x); Gn[k] = G[k]; }
+                for (int kk = 0; kk < K; ++kk) G[kk] = load_posq(spq + E0[kk].x);
+                // the window update a trip leaves to the next one (slot POOL: the dummy slot)
+                double pjx[K], pjy[K], pjz[K];
+                int pri[K];
+#pragma unroll
+                for (int kk = 0; kk < K; ++kk) { pjx[kk] = pjy[kk] = pjz[kk] = 0.0; pri[kk] = POOL; }
+                auto window_update = [&]() {
+                    if constexpr (GRAD && !EMIT) {
+                    double a0[K], a1[K], a2[K];
+#pragma unroll
+                    for (int kk = 0; kk < K; ++kk) { a0[kk] = acc[pri[kk]]; a1[kk] = acc[plane + pri[kk]]; a2[kk] = acc[2 * plane + pri[kk]]; }
+#pragma unroll
+                    for (int kk = 0; kk < K; ++kk) {
+                        // plain read-modify-write: this warp is the only writer and the partners of one trip are distinct
+                        // (K == 2: the two entries of a lane are 32 list places apart - distinct partners, distinct slots;
+                        // dummy entries all add 0 to the dummy slot)
+                        acc[pri[kk]] = a0[kk] + pjx[kk];
+                        acc[plane + pri[kk]] = a1[kk] + pjy[kk];
+                        acc[2 * plane + pri[kk]] = a2[kk] + pjz[kk];
+                    }
+                    }
+                };
 
-                // one trip: E0 / G are this trip's entries and records, E1 the next trip's entries (its records go to Gn)
-                do {
-                    if (nxt_pending) {                        // the atoms fetched during the previous trip go to their parking place
-                        __syncwarp();
-                        park_cluster(nxt);
-                        nxt_pending = false;
-                        __syncwarp();
-                    }
-                    if (t == 0) {                             // a new cluster starts with this trip (warp-uniform)
-                        ipos0 = C * (qb + il);
-                        const int ci_new = s_ci[il];
-                        pad_excl = 0;
-                        cb ^= 1;                              // the parked cluster becomes the current one
-                        cp = reinterpret_cast<const double*>(s_next + cb * 9);
-                        const int* nt = reinterpret_cast<const int*>(s_next + cb * 9 + 2 * C);
+                int k = 0;                                        // trip of the batch
+                // the trips of one cluster: E0 / G are this trip's entries and records, E1 the next trip's entries
+                auto run_trips = [&](auto ovf_tag, const int T) {
+                    constexpr bool OVF = decltype(ovf_tag)::value;
+#pragma unroll 1
+                    for (int t = 0; t < T; ++t, ++k) {
+                        window_update();                          // of the previous trip
+                        double dx[K][C], dy[K][C], dz[K][C], r2[K][C];
 #pragma unroll
-                        for (int a = 0; a < C; ++a) {
-                            qi2[a] = 2.0 * S.ele_scale * cp[4 * a + 3];          // doubled energies, see pair_terms
-                            const int ty = nt[a];
-                            trow[a] = (unsigned int)((ty & 0x7f) * S.n_types * (int)sizeof(PairConst));
-                            if (ty & kPadType) pad_excl |= 1u << (kMetaExclShift + a);
-                            gix[a] = giy[a] = giz[a] = 0.0;
-                        }
-                        if (GRAD && ci_new != cur_ci) {       // the sweep moves on: cells that left the windows are flushed
-                            int target = 0;
-                            if (lane < kClRowPitch) target = rowtab[ci_new * kClRowPitch + lane];
-                            flush_to(target);
-                            cur_ci = ci_new;
-                        }
-                        ci = ci_new;
-                        if (il + 1 < nq) {                    // the next cluster's atoms, one cluster ahead
-                            nxt = fetch_cluster(qb + il + 1);
-                            nxt_pending = true;
-                        }
-                        if (il + 2 < nq && 16 * lane < s_cnt[il + 2])      // and the list after the next one towards L2
-                            prefetch_l2(P.list + (size_t)(qb + il + 2) * P.cap + 16 * lane);
-                        n_cand_w += (unsigned long long)s_cnt[il] * C;
-                    }
-                    double dx[K][C], dy[K][C], dz[K][C], r2[K][C];
+                        for (int kk = 0; kk < K; ++kk) {
 #pragma unroll
-                    for (int k = 0; k < K; ++k) {
-#pragma unroll
-                        for (int a = 0; a < C; ++a) {
-                            // (the cluster's coordinates stay in shared memory: broadcast loads, 24 registers less)
-                            dx[k][a] = cp[4 * a] - G[k].x; dy[k][a] = cp[4 * a + 1] - G[k].y; dz[k][a] = cp[4 * a + 2] - G[k].z;
-                            // strict double, left-to-right, no FMA: Point3d.distance squared
-                            r2[k][a] = __dadd_rn(__dadd_rn(__dmul_rn(dx[k][a], dx[k][a]), __dmul_rn(dy[k][a], dy[k][a])),
-                                                 __dmul_rn(dz[k][a], dz[k][a]));
+                            for (int a = 0; a < C; ++a) {
+                                // (the cluster's coordinates stay in shared memory: broadcast loads, 24 registers less)
+                                dx[kk][a] = cp[4 * a] - G[kk].x; dy[kk][a] = cp[4 * a + 1] - G[kk].y; dz[kk][a] = cp[4 * a + 2] - G[kk].z;
+                                // strict double, left-to-right, no FMA: Point3d.distance squared
+                                r2[kk][a] = __dadd_rn(__dadd_rn(__dmul_rn(dx[kk][a], dx[kk][a]), __dmul_rn(dy[kk][a], dy[kk][a])),
+                                                      __dmul_rn(dz[kk][a], dz[kk][a]));
+                            }
                         }
-                    }
-                    // the pipeline: records of the next trip, entries of the one after it
-                    if (il1 < nq) {
-#pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            // the address carries a (never taken, for non-negative r2) dependence on r2, so that this load
-                            // is issued after the wait for this trip's operands and not before it (a NaN r2 with the sign
-                            // bit set moves the index by one: the arrays have a spare element, the result is NaN anyway)
-                            unsigned long long addr;
-                            asm("mad.wide.u32 %0, %1, 32, %2;" : "=l"(addr)
-                                : "r"(E1[k].x + ((unsigned int)__double2hiint(r2[k][0]) >> 31)), "l"(spq));
-                            Gn[k] = load_posq(reinterpret_cast<const PosQ*>(addr));
-                        }
-                    }
-                    uint2 E2[K];
-#pragma unroll
-                    for (int k = 0; k < K; ++k) E2[k] = make_uint2(0u, dummy_meta);
-                    if (il2 < nq) load_entries(il2, t2, E2);
-                    // arithmetic: K x C independent chains, interleaved statement by statement (pair_terms_n).  A pair that
-                    // does not count (beyond the cutoff, excluded, not later in the sorted order, padding, a lane beyond
-                    // the end of the list) has its two prefactors set to zero: r2 is clamped away from 0 and bounded by the
-                    // list construction, so every intermediate is finite and the products are exact zeros
-                    {
                         constexpr int NC = K * C;
                         double r2c[NC], qq2[NC], e1[NC], e2v[NC], f[NC];
                         PairConst pc[NC];
                         unsigned int em[K];
+                        // a pair that does not count (beyond the cutoff, excluded, not later in the sorted order, padding,
+                        // a dummy entry) has its two prefactors set to zero: r2 is clamped away from 0 and bounded by
+                        // the list construction, so every intermediate is finite and the products are exact zeros
 #pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            em[k] = E0[k].y | pad_excl;
-                            const unsigned int tj = ((em[k] >> kMetaTypeShift) & 127u) * (unsigned int)sizeof(PairConst);
+                        for (int kk = 0; kk < K; ++kk) {
+                            em[kk] = E0[kk].y | pad_excl;
+                            const unsigned int tj = ((em[kk] >> kMetaTypeShift) & 127u) * (unsigned int)sizeof(PairConst);
 #pragma unroll
                             for (int a = 0; a < C; ++a) {
-                                const int c = k * C + a;
-                                const bool on = !(r2[k][a] > S.r2_max) && !((em[k] >> (kMetaExclShift + a)) & 1u);
-                                const bool f14 = (em[k] >> (kMetaF14Shift + a)) & 1u;
-                                if (on) ++n_eval;
+                                const int c = kk * C + a;
+                                const bool on = !(r2[kk][a] > S.r2_max) && !((em[kk] >> (kMetaExclShift + a)) & 1u);
+                                const bool f14 = (em[kk] >> (kMetaF14Shift + a)) & 1u;
                                 if (EMIT) {
                                     if (on) {
-                                        const int oi = A.orig[ipos0 + a], oj = A.orig[E0[k].x];
+                                        const int oi = A.orig[ipos0 + a], oj = A.orig[E0[kk].x];
                                         const unsigned long long q = atomicAdd(P.cursor, 1ull);
                                         if ((long long)q < P.capacity) { P.out_i[q] = min(oi, oj); P.out_j[q] = max(oi, oj); P.out_14[q] = f14; }
                                     }
@@ -689,11 +678,25 @@ cl_pair_kernel(DeviceSystem S, CellArrays A, ClPairArgs P) {
                                 else pc[c] = *reinterpret_cast<const PairConst*>(reinterpret_cast<const unsigned char*>(S.table) + trow[a] + tj);
                                 pc[c].k1 = on ? pc[c].k1 : 0.0;
                                 // 0, 1 or 0.75 (1-4 pairs) as the high word of a double whose low word is zero
-                                const double sc = __hiloint2double(on ? (f14 ? 0x3fe80000 : 0x3ff00000) : 0, 0);
-                                qq2[c] = (qi2[a] * G[k].q) * sc;
-                                r2c[c] = clamp_r2(r2[k][a]);
+                                const unsigned int sch = on ? (f14 ? 0x3fe80000u : 0x3ff00000u) : 0u;
+                                n_eval += sch >> 29;              // 1 for both
+                                qq2[c] = (qi2[a] * G[kk].q) * __hiloint2double((int)sch, 0);
+                                r2c[c] = clamp_r2(r2[kk][a]);
                             }
                         }
+                        // the pipeline: records of the next trip (G is free now), entries of the one after it
+#pragma unroll
+                        for (int kk = 0; kk < K; ++kk) {
+                            // the address carries a (never taken, for non-negative r2) dependence on r2, so that this load
+                            // is issued after the wait for this trip's operands and not before it (a NaN r2 with the sign
+                            // bit set moves the index by one: the arrays have a spare element, the result is NaN anyway)
+                            unsigned long long addr;
+                            asm("mad.wide.u32 %0, %1, 32, %2;" : "=l"(addr)
+                                : "r"(E1[kk].x + ((unsigned int)__double2hiint(r2c[kk * C]) >> 31)), "l"(spq));
+                            G[kk] = load_posq(reinterpret_cast<const PosQ*>(addr));
+                        }
+                        uint2 E2[K];
+                        load_entries(k + 2, E2);
                         if (!EMIT) {
                             pair_terms_n<GRAD, NC>(r2c, pc, qq2, e1, e2v, f);
 #pragma unroll
@@ -701,39 +704,77 @@ cl_pair_kernel(DeviceSystem S, CellArrays A, ClPairArgs P) {
                         }
                         if (GRAD && !EMIT) {
 #pragma unroll
-                            for (int k = 0; k < K; ++k) {
+                            for (int kk = 0; kk < K; ++kk) {
                                 double gjx = 0, gjy = 0, gjz = 0;
 #pragma unroll
                                 for (int a = 0; a < C; ++a) {
-                                    const int c = k * C + a;
-                                    gix[a] = fma(f[c], dx[k][a], gix[a]);
-                                    giy[a] = fma(f[c], dy[k][a], giy[a]);
-                                    giz[a] = fma(f[c], dz[k][a], giz[a]);
-                                    gjx = fma(-f[c], dx[k][a], gjx);
-                                    gjy = fma(-f[c], dy[k][a], gjy);
-                                    gjz = fma(-f[c], dz[k][a], gjz);
+                                    const int c = kk * C + a;
+                                    gix[a] = fma(f[c], dx[kk][a], gix[a]);
+                                    giy[a] = fma(f[c], dy[kk][a], giy[a]);
+                                    giz[a] = fma(f[c], dz[kk][a], giz[a]);
+                                    gjx = fma(-f[c], dx[kk][a], gjx);
+                                    gjy = fma(-f[c], dy[kk][a], gjy);
+                                    gjz = fma(-f[c], dz[kk][a], gjz);
                                 }
-                                // the partner's window slot: plain read-modify-write - this warp is the only writer and the
-                                // partners of one trip are distinct (lanes beyond the list add 0 to the dummy slot)
-                                int ri = (int)(em[k] & kMetaSlotMask);
-                                if (__any_sync(FULL, (em[k] & kMetaOvf) != 0)) {  // rare: a row window denser than its ring
-                                    if (em[k] & kMetaOvf) {                       // atomics (order not fixed)
-                                        atomicAdd(P.gj_ovf + 3 * (size_t)E0[k].x, gjx);
-                                        atomicAdd(P.gj_ovf + 3 * (size_t)E0[k].x + 1, gjy);
-                                        atomicAdd(P.gj_ovf + 3 * (size_t)E0[k].x + 2, gjz);
+                                int ri = (int)(em[kk] & kMetaSlotMask);
+                                if (OVF) {                        // a row window denser than its ring: atomics (order not fixed)
+                                    if (em[kk] & kMetaOvf) {
+                                        atomicAdd(P.gj_ovf + 3 * (size_t)E0[kk].x, gjx);
+                                        atomicAdd(P.gj_ovf + 3 * (size_t)E0[kk].x + 1, gjy);
+                                        atomicAdd(P.gj_ovf + 3 * (size_t)E0[kk].x + 2, gjz);
                                         A.flags[2] = 1;
-                                        ri = POOL;                                // and nothing to the window
+                                        ri = POOL;                // and nothing to the window
                                         gjx = gjy = gjz = 0.0;
                                     }
                                 }
-                                acc[ri] += gjx;
-                                acc[plane + ri] += gjy;
-                                acc[2 * plane + ri] += gjz;
+                                pjx[kk] = gjx; pjy[kk] = gjy; pjz[kk] = gjz; pri[kk] = ri;
                             }
                         }
+#pragma unroll
+                        for (int kk = 0; kk < K; ++kk) { E0[kk] = E1[kk]; E1[kk] = E2[kk]; }
                     }
-                    // (the window updates of consecutive trips stay in program order: one warp, in-order shared-memory pipe)
-                    if (t + 1 == T && GRAD && !EMIT) {            // the cluster is complete: reduce its i-side sums over the warp
+                };
+
+                for (int il = 0; il < nq; ++il) {
+                    // ---- a new cluster: the parked atoms become the current ones
+                    ipos0 = C * (qb + il);
+                    const int cnt_raw = s_cnt[il];
+                    const int cnt = cnt_raw & 0x3fffffff;
+                    const int ci_new = s_ci[il];
+                    pad_excl = 0;
+                    cb ^= 1;
+                    cp = reinterpret_cast<const double*>(s_next + cb * 9);
+                    const int* nt = reinterpret_cast<const int*>(s_next + cb * 9 + 2 * C);
+#pragma unroll
+                    for (int a = 0; a < C; ++a) {
+                        qi2[a] = 2.0 * S.ele_scale * cp[4 * a + 3];              // doubled energies, see pair_terms
+                        const int ty = nt[a];
+                        trow[a] = (unsigned int)((ty & 0x7f) * S.n_types * (int)sizeof(PairConst));
+                        if (ty & kPadType) pad_excl |= 1u << (kMetaExclShift + a);
+                        gix[a] = giy[a] = giz[a] = 0.0;
+                    }
+                    if (il + 1 < nq) nxt = fetch_cluster(qb + il + 1);           // the next cluster's atoms, one cluster ahead
+                    if (il + 2 < nq && 16 * lane < (s_cnt[il + 2] & 0x3fffffff)) // and the list after the next one towards L2
+                        prefetch_l2(P.list + (size_t)(qb + il + 2) * P.cap + 16 * lane);
+                    if (GRAD && ci_new != cur_ci) {               // the sweep moves on: cells that left the windows are flushed
+                        window_update();                          // (the last trip's update first)
+#pragma unroll
+                        for (int kk = 0; kk < K; ++kk) { pjx[kk] = pjy[kk] = pjz[kk] = 0.0; pri[kk] = POOL; }
+                        __syncwarp();
+                        flush(cur_ci, ci_new);
+                        cur_ci = ci_new;
+                    }
+                    n_cand_w += (unsigned long long)cnt * C;
+                    const int T = min(max(1, (cnt + F::kSpan - 1) / F::kSpan), kClTripTab);
+                    if (cnt_raw & 0x40000000) run_trips(std::true_type{}, T);
+                    else run_trips(std::false_type{}, T);
+                    // ---- the cluster is complete
+                    if (il + 1 < nq) {                            // park the atoms fetched at its start
+                        __syncwarp();
+                        park_cluster(nxt);
+                        __syncwarp();
+                    }
+                    if (GRAD && !EMIT) {                          // its i-side sums over the warp
                         constexpr int NV = C == 2 ? 8 : 16;
                         double v[NV];
 #pragma unroll
@@ -745,20 +786,12 @@ cl_pair_kernel(DeviceSystem S, CellArrays A, ClPairArgs P) {
                         if ((lane & (32 / NV - 1)) == 0 && vi < 3 * C)
                             P.gi[3 * (size_t)ipos0 + vi] = v[0];
                     }
-                    // shift the pipeline by one trip
-                    il = il1; t = t1; T = T1;
-                    il1 = il2; t1 = t2; T1 = T2;
-                    advance(il2, t2, T2);
-#pragma unroll
-                    for (int k = 0; k < K; ++k) { E0[k] = E1[k]; E1[k] = E2[k]; G[k] = Gn[k]; }
-                } while (il < nq);
-                (void)ci;
+                }
+                window_update();                                  // the batch's last trip
+                qb += nq;
             }
-            {   // the segment is done: everything still in the windows goes out
-                int target = 0;
-                if (my_rowbase >= 0) target = A.start[my_rowbase + min(xb - 1 + g.reach, g.nx - 1) + 1];
-                flush_to(target);
-            }
+            __syncwarp();
+            flush(cur_ci, xb - xa);                               // the segment is done: everything still in the windows goes out
         }
         if (!EMIT) {
             ev = 0.5 * warp_sum(ev);                              // energies were accumulated doubled (pair_terms)
@@ -945,7 +978,7 @@ template <int C>
 inline int cl_run_lists_t(CellPlan& p, const DeviceSystem& ds, cudaStream_t st, uint64_t& launches, std::string& err) {
     ClListArgs A{};
     A.list = p.d_clist; A.count = p.d_count; A.cap = p.list_cap; A.ccap = p.cluster_cap; A.rank = p.rank; A.world = p.world;
-    A.layout = p.d_layout;
+    A.layout = p.d_layout; A.pool = p.arr.ring;
     const int grid = p.sms * kClListMinBlocks;
     const long long resident = (long long)grid * kListWarps;
     A.parts = (int)std::max(1ll, std::min(8ll, 2 * resident * 12 / std::max(1, ds.n)));
