@@ -327,7 +327,7 @@ int build_bonded_plan(jme_handle* h) {
 
 // atoms from which the cutoff path evaluates cluster lists with Newton's third law instead of per-atom lists (below,
 // the sweep of a few hundred segments leaves most of the chip idle; measured crossover)
-constexpr int64_t kClusterPathMinAtoms = 150000;
+constexpr int64_t kClusterPathMinAtoms = 90000;
 
 int choose_path(const jme_handle* h) {
     if (h->path == JME_PATH_ALLPAIRS) return JME_PATH_ALLPAIRS;
