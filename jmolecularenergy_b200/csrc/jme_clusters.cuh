@@ -972,10 +972,14 @@ inline int cl_configure(CellPlan& p, const DeviceSystem& ds, std::string& err) {
     p.cl_warps = kClWarps;
     p.cl_smem_grad = tb + kClWarps * cl_warp_smem(true, (int)pool);
     p.cl_smem_energy = tb + kClWarps * cl_warp_smem(false, (int)pool);
-    // about four segments per resident warp of THIS rank's shard (the shards of a multi-GPU job are 1 / world of the
-    // segments each: with the single-GPU segment length a rank at N = 4 had 1.6 segments per warp and its pair
+    // segments per resident warp: eight on one GPU (measured on 10^6 ions: segments of 12 / 11 / 8 / 6 / 5 cells give a
+    // pair sweep of 1.74 / 1.72 / 1.68 / 1.68 / 1.69 ms - shorter segments balance the warps better, longer ones flush
+    // their windows less often), and four per warp of THIS rank's shard in a multi-GPU job (the shards are 1 / world of
+    // the segments each: with the single-GPU segment length a rank at N = 4 had 1.6 segments per warp and its pair
     // kernel ran 45 % over its share)
-    p.arr.seg_target = 4 * p.sms * kClWarps * std::max(1, p.world);
+    int seg_mult = std::max(8, 4 * std::max(1, p.world));
+    if (const char* e = std::getenv("JME_SEG_MULT")) seg_mult = std::max(1, std::atoi(e));      // (development knob)
+    p.arr.seg_target = seg_mult * p.sms * kClWarps;
     return JME_OK;
 }
 
