@@ -261,6 +261,8 @@ def main():
     ap.add_argument("--workload", default="ions1m", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: coordinate / gradient exchange over NVLink peer memory (jme_peer_*) or NCCL collectives")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -313,8 +315,7 @@ def main():
             ev.set_coords(xyz_dev)            # AoS -> SoA on the device; invalidates the cell sort
             ev.evaluate_into(out, True)       # kernels on the current stream
         else:
-            ev.set_coords_owned(xyz_own_dev, xyz_full)
-            ev.evaluate_owned_into(out_full, grad_own)
+            ev.step_owned(xyz_own_dev, out_full, grad_own, xyz_full)
 
     def barrier():
         if world > 1:
@@ -328,6 +329,8 @@ def main():
     else:
         ev.set_coords_owned(xyz_own_dev, xyz_full)
     ev.prime()
+    if world > 1 and args.exchange == "peer":
+        ev.open_peer_exchange()            # from here on step_owned goes over NVLink peer memory, not through NCCL
     for _ in range(args.warmup):
         step_device()
     barrier()
@@ -448,8 +451,7 @@ def main():
             # pinned host rows of the owned atoms -> device, all-gather over NVLink, evaluation, reduction,
             # energies + owned gradient rows -> pinned host
             xyz_own_dev.copy_(host_own_xyz, non_blocking=True)
-            ev.set_coords_owned(xyz_own_dev, xyz_full)
-            ev.evaluate_owned_into(out_full, grad_own)
+            ev.step_owned(xyz_own_dev, out_full, grad_own, xyz_full)
             host_own_out[:10].copy_(out_full[:10], non_blocking=True)
             host_own_out[10:].copy_(grad_own, non_blocking=True)
             torch.cuda.synchronize()
@@ -489,8 +491,8 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "description": cfg["desc"], "atoms": n, "pairs_per_step": pairs,
-                       "cutoff": cfg["cutoff"], "path": cfg["path"], "parallelism": (f"atom-row shards x{world}; all-gather of coordinates, all-reduce of energies, "
-                                       f"reduce-scatter of the gradient (every rank ends with the rows of its own atoms)")
+                       "cutoff": cfg["cutoff"], "path": cfg["path"], "parallelism": (f"atom-row shards x{world}; " + ("coordinate slices pushed to / gradient rows pulled from every rank over NVLink peer memory (jme_peer_step)" if args.exchange == "peer" else "all-gather of coordinates, all-reduce of energies, reduce-scatter of the gradient (NCCL)") +
+                                       " - every rank ends with the rows of its own atoms")
                        if world > 1 else "single GPU",
                        "scheme": {1: "all-pairs tiles", 3: "cell lists, per-atom survivor lists", 4: "cell lists, cluster lists + Newton's third law"}.get(int(L.jme_active_path(st.h)), "?"),
                        "l2": "256 MiB written between timed steps (L2 flush); step = marshal + cell build + pairs + bonded + reduce"},

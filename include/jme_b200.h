@@ -170,6 +170,26 @@ int jme_adam_minimize(jme_handle_t* h, int max_steps, double step_size, double t
                       double epsilon, double* xyz_inout, int64_t* energy_calls, int* steps_done, double* step_energies,
                       int capacity);
 
+/* ---- owner-mode exchange of a multi-GPU job over NVLink peer memory ----
+ * One process per GPU, every rank owns chunk = jme_peer_chunk() consecutive atoms (by original index; the last
+ * ranks' chunks are padded).  Each rank creates a communicator on its current device, hands the 64-byte handle of
+ * its exported block (a cudaIpcMemHandle_t) to the others by whatever means the host has (MPI, torch.distributed,
+ * a JVM-side socket), and opens theirs (`handles`: world x 64 bytes in rank order; the own entry is ignored).
+ * jme_peer_step then replaces all-gather + all-reduce + reduce-scatter around the local evaluation of `h`
+ * (jme_set_shard(h, rank, world) already applied): d_xyz_own = device AoS [chunk][3] of this rank's atoms,
+ * d_grad_own receives [chunk][3], d_header the 10 job-wide doubles of jme_eval_device's header; everything is
+ * enqueued on h's stream, nothing is synchronised.  Every rank must call it the same number of times.  The sum
+ * over ranks runs in rank order (reproducible).  A rank that waits more than 4 s for a peer gives up and the total
+ * ([0] of the header) is NaN. */
+typedef struct jme_peer_comm jme_peer_comm_t;
+int jme_peer_create(int rank, int world, int64_t n_atoms, jme_peer_comm_t** out);
+int64_t jme_peer_chunk(const jme_peer_comm_t* c);
+int jme_peer_handle(const jme_peer_comm_t* c, void* handle64);
+int jme_peer_open(jme_peer_comm_t* c, const void* handles);
+int jme_peer_step(jme_peer_comm_t* c, jme_handle_t* h, const double* d_xyz_own, double* d_grad_own, double* d_header);
+const char* jme_peer_last_error(const jme_peer_comm_t* c);
+void jme_peer_destroy(jme_peer_comm_t* c);
+
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 uint64_t jme_launch_count(const jme_handle_t* h);
 

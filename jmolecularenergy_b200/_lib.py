@@ -22,6 +22,8 @@ EXPORTS = (
     "jme_set_coords_device", "jme_eval_device", "jme_eval_out_size", "jme_launch_count",
     "jme_measure_fp64_peak", "jme_enumerate_terms", "jme_exclusions", "jme_set_profiling", "jme_profile_read",
     "jme_gd_minimize", "jme_adam_minimize", "jme_active_path",
+    "jme_peer_create", "jme_peer_chunk", "jme_peer_handle", "jme_peer_open", "jme_peer_step", "jme_peer_last_error",
+    "jme_peer_destroy",
 )
 
 _lib = None
@@ -98,5 +100,19 @@ def lib():
                                       c_i32p, c_i64p, c_i32p, c_i64p, c_i32p, c_i64p]
     L.jme_exclusions.restype = C.c_int
     L.jme_exclusions.argtypes = [C.c_int64, C.c_int64, c_i32p, c_i32p, c_i64p, c_i32p, c_u8p, C.c_int64, c_i64p]
+    L.jme_peer_create.restype = C.c_int
+    L.jme_peer_create.argtypes = [C.c_int, C.c_int, C.c_int64, C.POINTER(H)]
+    L.jme_peer_chunk.restype = C.c_int64
+    L.jme_peer_chunk.argtypes = [H]
+    L.jme_peer_handle.restype = C.c_int
+    L.jme_peer_handle.argtypes = [H, C.c_void_p]
+    L.jme_peer_open.restype = C.c_int
+    L.jme_peer_open.argtypes = [H, C.c_void_p]
+    L.jme_peer_step.restype = C.c_int
+    L.jme_peer_step.argtypes = [H, H, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.jme_peer_last_error.restype = C.c_char_p
+    L.jme_peer_last_error.argtypes = [H]
+    L.jme_peer_destroy.restype = None
+    L.jme_peer_destroy.argtypes = [H]
     _lib = L
     return L

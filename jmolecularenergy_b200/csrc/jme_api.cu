@@ -15,6 +15,7 @@
 #include "../../include/jme_b200.h"
 #include "jme_cells.cuh"
 #include "jme_clusters.cuh"
+#include "jme_peer.cuh"
 #include "jme_host.hpp"
 #include "jme_kernels.cuh"
 
@@ -1096,6 +1097,109 @@ int jme_exclusions(int64_t n_atoms, int64_t n_bonds, const int32_t* bond_i, cons
             is14[e] = (ent[e] & kFlag14) ? 1 : 0;
         }
     return JME_OK;
+}
+
+// ---- owner-mode exchange over NVLink peer memory (jme_peer.cuh) ----------------------------------------------
+struct jme_peer_comm {
+    int rank = 0, world = 1, device = 0;
+    int64_t n = 0, chunk = 0;              // atoms, atoms per rank (even)
+    size_t xyz_off = 0, out_off = 0, total = 0;
+    unsigned char* base = nullptr;         // this rank's exported block
+    unsigned char* peer[kPeerMaxWorld] = {};
+    bool opened = false;
+    unsigned long long seq = 0;
+    int sms = 148;
+    std::string err;
+};
+
+int jme_peer_create(int rank, int world, int64_t n_atoms, jme_peer_comm_t** out) {
+    if (!out || world < 1 || world > kPeerMaxWorld || rank < 0 || rank >= world || n_atoms < 0) return JME_ERR_INVALID;
+    *out = nullptr;
+    jme_peer_comm* c = new (std::nothrow) jme_peer_comm();
+    if (!c) return JME_ERR_NOMEM;
+    c->rank = rank; c->world = world; c->n = n_atoms;
+    c->chunk = ((n_atoms + world - 1) / world + 1) / 2 * 2;
+    const size_t xyz_bytes = ((size_t)3 * c->chunk * world * sizeof(double) + 255) / 256 * 256;
+    const size_t out_bytes = (((size_t)kOutHeader + (size_t)3 * c->chunk * world) * sizeof(double) + 255) / 256 * 256;
+    c->xyz_off = kPeerCtrlBytes;
+    c->out_off = c->xyz_off + xyz_bytes;
+    c->total = c->out_off + out_bytes;
+    cudaError_t e = cudaGetDevice(&c->device);
+    if (e == cudaSuccess) e = cudaMalloc(&c->base, c->total);
+    if (e == cudaSuccess) e = cudaMemset(c->base, 0, c->total);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, c->device);
+    if (e != cudaSuccess) { if (c->base) cudaFree(c->base); delete c; return e == cudaErrorMemoryAllocation ? JME_ERR_NOMEM : JME_ERR_CUDA; }
+    c->peer[rank] = c->base;
+    *out = c;
+    return JME_OK;
+}
+
+int64_t jme_peer_chunk(const jme_peer_comm_t* c) { return c ? c->chunk : 0; }
+const char* jme_peer_last_error(const jme_peer_comm_t* c) { return c ? c->err.c_str() : "null communicator"; }
+
+int jme_peer_handle(const jme_peer_comm_t* c, void* handle64) {
+    if (!c || !handle64) return JME_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t hd;
+    if (cudaIpcGetMemHandle(&hd, c->base) != cudaSuccess) { cudaGetLastError(); return JME_ERR_CUDA; }
+    std::memcpy(handle64, &hd, 64);
+    return JME_OK;
+}
+
+int jme_peer_open(jme_peer_comm_t* c, const void* handles) {
+    if (!c || !handles) return JME_ERR_INVALID;
+    if (c->opened) return JME_OK;
+    for (int p = 0; p < c->world; ++p) {
+        if (p == c->rank) continue;
+        cudaIpcMemHandle_t hd;
+        std::memcpy(&hd, static_cast<const unsigned char*>(handles) + 64 * (size_t)p, 64);
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            c->err = std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(p) + "): " + cudaGetErrorString(e);
+            cudaGetLastError();
+            return JME_ERR_CUDA;
+        }
+        c->peer[p] = static_cast<unsigned char*>(ptr);
+    }
+    c->opened = true;
+    return JME_OK;
+}
+
+// One owner-mode step, enqueued on the evaluation handle's stream: d_xyz_own = the 3 * chunk coordinates of this
+// rank's atoms, d_grad_own receives their 3 * chunk gradient doubles, d_header the job-wide 10-double header.
+int jme_peer_step(jme_peer_comm_t* c, jme_handle_t* h, const double* d_xyz_own, double* d_grad_own, double* d_header) {
+    if (!c || !h || !d_xyz_own || !d_grad_own || !d_header) return JME_ERR_INVALID;
+    if (!c->opened && c->world > 1) return fail(h, JME_ERR_INVALID, "peer communicator: jme_peer_open first");
+    if (h->hs.n != c->n || h->world != c->world || h->rank != c->rank) return fail(h, JME_ERR_INVALID, "peer communicator and handle disagree (atoms / shard)");
+    const unsigned long long seq = ++c->seq;
+    PeerPtrs P{};
+    for (int p = 0; p < c->world; ++p) P.base[p] = c->peer[p];
+    const long long slice = 3 * c->chunk;
+    cudaStream_t st = h->stream;
+    const int bx = (int)std::max<long long>(1, std::min<long long>(2 * c->sms / c->world + 1, (slice / 2 + 255) / 256));
+    peer_push_kernel<<<dim3(bx, c->world), 256, 0, st>>>(P, c->rank, c->xyz_off, slice, d_xyz_own, seq);
+    peer_wait_kernel<<<1, 32, 0, st>>>(c->base, kPeerPushSeq, c->world, seq);
+    h->launches += 2;
+    int rc = jme_set_coords_device(h, reinterpret_cast<const double*>(c->base + c->xyz_off), c->n);
+    if (rc) return rc;
+    if ((rc = jme_eval_device(h, 1, reinterpret_cast<double*>(c->base + c->out_off)))) return rc;
+    peer_done_kernel<<<1, 32, 0, st>>>(P, c->rank, c->world, seq);
+    const int gx = (int)std::max<long long>(1, std::min<long long>(2 * c->sms, (slice / 2 + 255) / 256));
+    peer_pull_kernel<<<gx, 256, 0, st>>>(P, c->rank, c->world, c->out_off, slice, d_grad_own, d_header, seq);
+    h->launches += 2;
+    JME_CUDA(h, cudaGetLastError());
+    return JME_OK;
+}
+
+void jme_peer_destroy(jme_peer_comm_t* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int p = 0; p < c->world; ++p)
+        if (p != c->rank && c->peer[p]) cudaIpcCloseMemHandle(c->peer[p]);
+    if (c->base) cudaFree(c->base);
+    delete c;
 }
 
 }  // extern "C"

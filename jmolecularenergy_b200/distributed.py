@@ -13,7 +13,9 @@ streams and the process group.
 Two result layouts: replicated (``evaluate_into``: every rank ends with everything, one all-reduce of 24 N + 80
 bytes) and owner mode (``set_coords_owned`` / ``evaluate_owned_into``: a rank supplies and receives only the rows of
 the atoms it owns - all-gather of the coordinates, all-reduce of the 10-double header, reduce-scatter of the
-gradient).  bench.py uses owner mode for N > 1.
+gradient) - or, after ``open_peer_exchange``, ``step_owned`` with the same meaning and no collective: the ranks store
+their coordinate slices into each other's buffers and read each other's partial gradient rows over NVLink peer memory
+(``jme_peer_*``, csrc/jme_peer.cuh).  bench.py uses that for N > 1 (``--exchange nccl`` for the collectives).
 """
 from __future__ import annotations
 
@@ -58,6 +60,7 @@ class ShardedMMFF94:
         self.rank, self.world = rank, world
         self.local_eval = local_eval
         self.state = None
+        self._peer = None
         if local_eval is None:
             from . import _lib
             from .forcefield import _GpuState
@@ -130,8 +133,8 @@ class ShardedMMFF94:
     # moves 1/world of the bytes of the replicated mode over PCIe and half the bytes over NVLink.
     @property
     def chunk(self) -> int:
-        """Atoms per rank in owner mode (the last ranks' chunks are padded)."""
-        return (self.n + self.world - 1) // self.world
+        """Atoms per rank in owner mode (even; the last ranks' chunks are padded) - ``jme_peer_chunk``."""
+        return ((self.n + self.world - 1) // self.world + 1) // 2 * 2
 
     def owned_range(self):
         a0 = min(self.n, self.rank * self.chunk)
@@ -175,6 +178,44 @@ class ShardedMMFF94:
         else:
             grad_own.copy_(grad_full)
 
+    # ---- owner mode over NVLink peer memory (include/jme_b200.h: jme_peer_*; csrc/jme_peer.cuh) -----------
+    def open_peer_exchange(self) -> None:
+        """Create this rank's exported block, swap the 64-byte IPC handles through the process group (the only use
+        of NCCL on this path) and map the peers' blocks.  Collective: every rank calls it."""
+        if self.local_eval is not None or self.world == 1 or self._peer is not None:
+            return
+        torch, dist, L = self.torch, self.dist, self.L
+        comm = C.c_void_p()
+        self.state.check(L.jme_peer_create(self.rank, self.world, self.n, C.byref(comm)))
+        if int(L.jme_peer_chunk(comm)) != self.chunk:
+            raise RuntimeError("chunk size mismatch between distributed.py and jme_peer_chunk")
+        mine = (C.c_ubyte * 64)()
+        self.state.check(L.jme_peer_handle(comm, mine))
+        t = torch.tensor(list(mine), dtype=torch.uint8, device=self.device)
+        every = torch.empty(64 * self.world, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(every, t)
+        buf = (C.c_ubyte * (64 * self.world)).from_buffer_copy(bytes(every.cpu().numpy().tobytes()))
+        rc = L.jme_peer_open(comm, buf)
+        if rc != 0:
+            msg = L.jme_peer_last_error(comm).decode()
+            L.jme_peer_destroy(comm)
+            raise RuntimeError(f"jme_peer_open failed ({rc}): {msg}")
+        dist.barrier()                      # everybody has mapped everybody before the first store
+        self._peer = comm
+
+    def step_owned(self, xyz_own, out_full, grad_own, xyz_full=None) -> None:
+        """One owner-mode step: ``xyz_own`` (3 * chunk doubles on this rank's device) in, ``out_full[:10]`` = the
+        job-wide header and ``grad_own`` (3 * chunk) out.  Over peer memory when ``open_peer_exchange`` was called,
+        else through the process group (all-gather, all-reduce, reduce-scatter; needs ``xyz_full``)."""
+        if self._peer is not None:
+            self._bind_stream()
+            self.state.check(self.L.jme_peer_step(self._peer, self.state.h, C.c_void_p(xyz_own.data_ptr()),
+                                                  C.c_void_p(grad_own.data_ptr()), C.c_void_p(out_full.data_ptr())))
+            self._keep = (xyz_own, out_full, grad_own)
+        else:
+            self.set_coords_owned(xyz_own, xyz_full)
+            self.evaluate_owned_into(out_full, grad_own)
+
     def evaluate(self, gradient: bool = True) -> Dict[str, object]:
         out = self.new_output(gradient)
         self.evaluate_into(out, gradient)
@@ -186,6 +227,9 @@ class ShardedMMFF94:
         return 0 if self.state is None else int(self.L.jme_launch_count(self.state.h))
 
     def close(self) -> None:
+        if self._peer is not None:
+            self.L.jme_peer_destroy(self._peer)
+            self._peer = None
         if self.state is not None:
             self.state.close()
             self.state = None

@@ -1,6 +1,6 @@
 """Worker of tests/test_multi_gpu.py: one rank per GPU under torchrun (NCCL).  Every rank evaluates its shard of a
-system through libjme_b200.so (owner mode: all-gather of the coordinates, all-reduce of the energies, reduce-scatter of
-the gradient) and compares what it ends up with - the job-wide energies / pair count and the gradient rows of the atoms
+system through libjme_b200.so (owner mode, first with the collectives - all-gather of the coordinates, all-reduce of the
+energies, reduce-scatter of the gradient - then over NVLink peer memory, jme_peer_step) and compares what it ends up with - the job-wide energies / pair count and the gradient rows of the atoms
 it owns - with the CPU oracle.  Prints one JSON line per rank and exits non-zero on a mismatch."""
 import json
 import os
@@ -43,6 +43,22 @@ def main():
             ev.set_coords_owned(xyz_own, xyz_full)
             ev.evaluate_owned_into(out_full, grad_own)
         torch.cuda.synchronize()
+        # the same step over NVLink peer memory (jme_peer_step) must reproduce the collectives' result: energies to
+        # rounding (another order of the sum over ranks), and itself bit for bit when repeated
+        nccl_head, nccl_grad = out_full[:10].clone(), grad_own.clone()
+        ev.open_peer_exchange()
+        peer_runs = []
+        for _ in range(3):
+            out_full.zero_()
+            grad_own.zero_()
+            ev.step_owned(xyz_own, out_full, grad_own)
+            torch.cuda.synchronize()
+            peer_runs.append((out_full[:10].clone(), grad_own.clone()))
+        peer_same = all(torch.equal(peer_runs[0][0], h) and torch.equal(peer_runs[0][1], g_) for h, g_ in peer_runs[1:])
+        scale = float(nccl_grad.abs().max().item()) + 1e-300
+        peer_vs_nccl = max(float(((peer_runs[0][0][:8] - nccl_head[:8]).abs() / nccl_head[:8].abs().clamp_min(1e-3)).max().item()),
+                           float((peer_runs[0][1] - nccl_grad).abs().max().item()) / scale)
+        peer_ok = peer_same and peer_vs_nccl <= 1e-12 and float(peer_runs[0][0][8].item()) == float(nccl_head[8].item())
         got = unpack(out_full.cpu().numpy(), n, False)
         g = grad_own.cpu().numpy()[:3 * (a1 - a0)].reshape(-1, 3)
         e_err = max(abs(got[k] - ref[k]) / max(abs(ref[k]), abs(ref["total"]), 1e-3)
@@ -50,12 +66,13 @@ def main():
         gr = ref["gradient"][a0:a1]
         floor = 1e-10 * max(1.0, float(np.abs(ref["gradient"]).max()))
         g_err = float(np.max(np.abs(g - gr) / (np.abs(gr) + floor / 1e-8))) if a1 > a0 else 0.0
-        case_ok = e_err <= 1e-10 and g_err <= 1e-8 and got["pairs"] == ref["pairs"]
+        case_ok = e_err <= 1e-10 and g_err <= 1e-8 and got["pairs"] == ref["pairs"] and peer_ok
         ok = ok and case_ok
         worst["energy"] = max(worst["energy"], e_err)
         worst["gradient"] = max(worst["gradient"], g_err)
         print(json.dumps({"rank": rank, "case": label, "ok": case_ok, "energy_rel_err": e_err, "gradient_rel_err": g_err,
-                          "pairs": got["pairs"], "pairs_ref": ref["pairs"]}), flush=True)
+                          "pairs": got["pairs"], "pairs_ref": ref["pairs"], "peer_repeat_identical": peer_same,
+                          "peer_vs_collectives": peer_vs_nccl}), flush=True)
         ev.close()
     flag = torch.tensor([0.0 if ok else 1.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MAX)
