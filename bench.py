@@ -329,8 +329,10 @@ def main():
     else:
         ev.set_coords_owned(xyz_own_dev, xyz_full)
     ev.prime()
-    if world > 1 and args.exchange == "peer":
-        ev.open_peer_exchange()            # from here on step_owned goes over NVLink peer memory, not through NCCL
+    exchange = "single GPU"
+    if world > 1:
+        # from here on step_owned goes over NVLink peer memory, not through NCCL (unless the GPUs cannot map each other)
+        exchange = "peer" if args.exchange == "peer" and ev.open_peer_exchange() else "nccl"
     for _ in range(args.warmup):
         step_device()
     barrier()
@@ -431,7 +433,7 @@ def main():
         t = torch.tensor(acc, dtype=torch.float64, device=dev) / n_ph
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         phases = {k: float(v) for k, v in zip(names, t.tolist())}
-        phases["unit"] = "ms, max over ranks, measured in a separate loop after the timed region"
+        phases["unit"] = "ms, max over ranks; the phases of the step with NCCL collectives, measured in a separate loop after the timed region (the timed step itself uses the exchange named in config.parallelism)"
 
     # ---- end to end through the host-buffer C ABI (rank-local; for N > 1 the partial results are reduced
     #      on the device and copied back, so the host round trip is included on every rank)
@@ -491,7 +493,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "description": cfg["desc"], "atoms": n, "pairs_per_step": pairs,
-                       "cutoff": cfg["cutoff"], "path": cfg["path"], "parallelism": (f"atom-row shards x{world}; " + ("coordinate slices pushed to / gradient rows pulled from every rank over NVLink peer memory (jme_peer_step)" if args.exchange == "peer" else "all-gather of coordinates, all-reduce of energies, reduce-scatter of the gradient (NCCL)") +
+                       "cutoff": cfg["cutoff"], "path": cfg["path"], "parallelism": (f"atom-row shards x{world}; " + ("coordinate slices pushed to / gradient rows pulled from every rank over NVLink peer memory (jme_peer_step)" if exchange == "peer" else "all-gather of coordinates, all-reduce of energies, reduce-scatter of the gradient (NCCL)" + (f"; peer mapping failed: {ev.peer_error}" if ev.peer_error else "")) +
                                        " - every rank ends with the rows of its own atoms")
                        if world > 1 else "single GPU",
                        "scheme": {1: "all-pairs tiles", 3: "cell lists, per-atom survivor lists", 4: "cell lists, cluster lists + Newton's third law"}.get(int(L.jme_active_path(st.h)), "?"),

@@ -61,6 +61,7 @@ class ShardedMMFF94:
         self.local_eval = local_eval
         self.state = None
         self._peer = None
+        self.peer_error = ""
         if local_eval is None:
             from . import _lib
             from .forcefield import _GpuState
@@ -179,29 +180,43 @@ class ShardedMMFF94:
             grad_own.copy_(grad_full)
 
     # ---- owner mode over NVLink peer memory (include/jme_b200.h: jme_peer_*; csrc/jme_peer.cuh) -----------
-    def open_peer_exchange(self) -> None:
+    def open_peer_exchange(self) -> bool:
         """Create this rank's exported block, swap the 64-byte IPC handles through the process group (the only use
-        of NCCL on this path) and map the peers' blocks.  Collective: every rank calls it."""
-        if self.local_eval is not None or self.world == 1 or self._peer is not None:
-            return
+        of NCCL on this path) and map the peers' blocks.  Collective: every rank calls it.  Returns False - on every
+        rank, with ``peer_error`` set - when some rank could not map a peer (no peer access between two of the GPUs,
+        IPC not permitted); ``step_owned`` then keeps using the collectives."""
+        if self.local_eval is not None or self.world == 1:
+            return False
+        if self._peer is not None:
+            return True
         torch, dist, L = self.torch, self.dist, self.L
         comm = C.c_void_p()
-        self.state.check(L.jme_peer_create(self.rank, self.world, self.n, C.byref(comm)))
-        if int(L.jme_peer_chunk(comm)) != self.chunk:
-            raise RuntimeError("chunk size mismatch between distributed.py and jme_peer_chunk")
+        self.peer_error = ""
+        rc = L.jme_peer_create(self.rank, self.world, self.n, C.byref(comm))
         mine = (C.c_ubyte * 64)()
-        self.state.check(L.jme_peer_handle(comm, mine))
+        if rc == 0:
+            rc = L.jme_peer_handle(comm, mine)
+        if rc != 0:
+            self.peer_error = f"jme_peer_create / jme_peer_handle failed ({rc})"
         t = torch.tensor(list(mine), dtype=torch.uint8, device=self.device)
         every = torch.empty(64 * self.world, dtype=torch.uint8, device=self.device)
         dist.all_gather_into_tensor(every, t)
-        buf = (C.c_ubyte * (64 * self.world)).from_buffer_copy(bytes(every.cpu().numpy().tobytes()))
-        rc = L.jme_peer_open(comm, buf)
-        if rc != 0:
-            msg = L.jme_peer_last_error(comm).decode()
-            L.jme_peer_destroy(comm)
-            raise RuntimeError(f"jme_peer_open failed ({rc}): {msg}")
-        dist.barrier()                      # everybody has mapped everybody before the first store
+        if rc == 0:
+            if int(L.jme_peer_chunk(comm)) != self.chunk:
+                raise RuntimeError("chunk size mismatch between distributed.py and jme_peer_chunk")
+            buf = (C.c_ubyte * (64 * self.world)).from_buffer_copy(every.cpu().numpy().tobytes())
+            rc = L.jme_peer_open(comm, buf)
+            if rc != 0:
+                self.peer_error = f"jme_peer_open failed ({rc}): {L.jme_peer_last_error(comm).decode()}"
+        ok = torch.tensor([1.0 if rc == 0 else 0.0], device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)    # also: everybody has mapped everybody before the first store
+        if ok.item() != 1.0:
+            if comm:
+                L.jme_peer_destroy(comm)
+            self.peer_error = self.peer_error or "another rank could not map its peers"
+            return False
         self._peer = comm
+        return True
 
     def step_owned(self, xyz_own, out_full, grad_own, xyz_full=None) -> None:
         """One owner-mode step: ``xyz_own`` (3 * chunk doubles on this rank's device) in, ``out_full[:10]`` = the
