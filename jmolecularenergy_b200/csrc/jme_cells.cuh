@@ -120,7 +120,13 @@ struct CellArrays {
 };
 
 // ---- 1. bounding box ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bbox_kernel(DeviceSystem S, double* __restrict__ part, int* __restrict__ flags) {
+__device__ void grid_setup(const double* part, int n_part, double cutoff, int max_cells, int seg_target, int rank, int world,
+                           GridParams* g);
+
+// per-block bounding boxes; the last block to finish (counter) reduces them and sets up the grid - one launch less
+// in a chain that is launch-latency bound for small systems
+__global__ void __launch_bounds__(256) bbox_kernel(DeviceSystem S, double* part, int* __restrict__ flags, int* __restrict__ done_ctr,
+                                                   double cutoff, int max_cells, int seg_target, int rank, int world, GridParams* g) {
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     bool bad = false;
     for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < S.n; a += gridDim.x * blockDim.x) {
@@ -147,12 +153,21 @@ __global__ void __launch_bounds__(256) bbox_kernel(DeviceSystem S, double* __res
         for (int w = 1; w < 8; ++w) v = threadIdx.x < 3 ? fmin(v, s[w][threadIdx.x]) : fmax(v, s[w][threadIdx.x]);
         part[6 * blockIdx.x + threadIdx.x] = v;
     }
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(done_ctr, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!s_last || threadIdx.x >= 32) return;
+    __threadfence();
+    grid_setup(part, (int)gridDim.x, cutoff, max_cells, seg_target, rank, world, g);
 }
 
-__global__ void grid_setup_kernel(const double* __restrict__ part, int n_part, double cutoff, int max_cells, int seg_target,
-                                  int rank, int world, GridParams* g) {
-    // one warp: lanes stride over the per-block bounding boxes, shuffle min/max, lane 0 derives the grid
-    const int lane = threadIdx.x;
+// one warp (the first warp of the last bbox block to finish): lanes stride over the per-block bounding boxes, shuffle
+// min / max, lane 0 derives the grid
+__device__ void grid_setup(const double* part, int n_part, double cutoff, int max_cells, int seg_target,
+                           int rank, int world, GridParams* g) {
+    const int lane = threadIdx.x & 31;
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     for (int b = lane; b < n_part; b += 32)
         for (int c = 0; c < 3; ++c) { lo[c] = fmin(lo[c], part[6 * b + c]); hi[c] = fmax(hi[c], part[6 * b + 3 + c]); }
@@ -294,22 +309,25 @@ __global__ void cell_assign_kernel(DeviceSystem S, const GridParams* __restrict_
 __global__ void __launch_bounds__(kScanBlock) scan_local_kernel(const GridParams* __restrict__ g, const int* __restrict__ count,
                                                                 int* __restrict__ start, int* __restrict__ block_sums, int pad) {
     const int total = g->ncell + 1;
-    const int base = blockIdx.x * kScanBlock;
-    if (base >= total) return;
     __shared__ int s[kScanBlock];
-    const int i = base + threadIdx.x;
-    // cells are padded to a multiple of `pad` sorted positions (cluster path): start[] runs over the padded sizes
-    const int v = i < total ? (count[i] + pad - 1) / pad * pad : 0;
-    s[threadIdx.x] = v;
-    __syncthreads();
-    for (int o = 1; o < kScanBlock; o <<= 1) {
-        const int t = threadIdx.x >= o ? s[threadIdx.x - o] : 0;
+    // (a fixed modest grid striding over the chunks: the cell count is known on the device only, and launching a
+    // block per chunk of the allocated maximum cost 7 us of empty blocks)
+    for (int base = blockIdx.x * kScanBlock; base < total; base += gridDim.x * kScanBlock) {
+        const int i = base + threadIdx.x;
+        // cells are padded to a multiple of `pad` sorted positions (cluster path): start[] runs over the padded sizes
+        const int v = i < total ? (count[i] + pad - 1) / pad * pad : 0;
         __syncthreads();
-        s[threadIdx.x] += t;
+        s[threadIdx.x] = v;
         __syncthreads();
+        for (int o = 1; o < kScanBlock; o <<= 1) {
+            const int t = threadIdx.x >= o ? s[threadIdx.x - o] : 0;
+            __syncthreads();
+            s[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < total) start[i] = s[threadIdx.x] - v;
+        if (threadIdx.x == kScanBlock - 1) block_sums[base / kScanBlock] = s[threadIdx.x];
     }
-    if (i < total) start[i] = s[threadIdx.x] - v;
-    if (threadIdx.x == kScanBlock - 1) block_sums[blockIdx.x] = s[threadIdx.x];
 }
 
 __global__ void __launch_bounds__(1024) scan_sums_kernel(const GridParams* __restrict__ g, int* __restrict__ block_sums) {
@@ -340,8 +358,7 @@ __global__ void __launch_bounds__(1024) scan_sums_kernel(const GridParams* __res
 __global__ void __launch_bounds__(kScanBlock) scan_add_kernel(const GridParams* __restrict__ g, int* __restrict__ start,
                                                               const int* __restrict__ block_sums) {
     const int total = g->ncell + 1;
-    const int i = blockIdx.x * kScanBlock + threadIdx.x;
-    if (i < total) start[i] += block_sums[blockIdx.x];
+    for (int i = blockIdx.x * kScanBlock + threadIdx.x; i < total; i += gridDim.x * kScanBlock) start[i] += block_sums[i / kScanBlock];
 }
 
 // ---- 3. sort -----------------------------------------------------------------------------------
@@ -1084,16 +1101,17 @@ inline int run_cell_sort(CellPlan& p, const DeviceSystem& ds, cudaStream_t st, u
     const int nb = (n + 255) / 256;
     const int scan_blocks = (a.max_cells + 1 + kScanBlock - 1) / kScanBlock;
     cudaMemsetAsync(a.work_ctr, 0, 8 * sizeof(int), st);          // work counters and flags
-    bbox_kernel<<<a.bbox_blocks, 256, 0, st>>>(ds, a.bbox_part, a.flags);
-    grid_setup_kernel<<<1, 32, 0, st>>>(a.bbox_part, a.bbox_blocks, p.cutoff, a.max_cells, a.seg_target, a.rank, a.world, a.grid);
+    bbox_kernel<<<a.bbox_blocks, 256, 0, st>>>(ds, a.bbox_part, a.flags, a.work_ctr + 2, p.cutoff, a.max_cells, a.seg_target, a.rank,
+                                               a.world, a.grid);
     zero_counts_kernel<<<std::min(592, (a.max_cells + 256) / 256), 256, 0, st>>>(a.grid, a.count, a.cursor);
     cell_assign_kernel<<<nb, 256, 0, st>>>(ds, a.grid, a.cell_of, a.count);
-    scan_local_kernel<<<scan_blocks, kScanBlock, 0, st>>>(a.grid, a.count, a.start, a.block_sums, a.pad);
+    const int scan_grid = std::min(scan_blocks, 2 * std::max(1, p.sms));
+    scan_local_kernel<<<scan_grid, kScanBlock, 0, st>>>(a.grid, a.count, a.start, a.block_sums, a.pad);
     scan_sums_kernel<<<1, 1024, 0, st>>>(a.grid, a.block_sums);
-    scan_add_kernel<<<scan_blocks, kScanBlock, 0, st>>>(a.grid, a.start, a.block_sums);
+    scan_add_kernel<<<scan_grid, kScanBlock, 0, st>>>(a.grid, a.start, a.block_sums);
     cell_scatter_kernel<<<nb, 256, 0, st>>>(n, a.cell_of, a.start, a.cursor, a.order_tmp, a.grid, a.rank, a.world);
     cell_rank_gather_kernel<<<nb, 256, 0, st>>>(ds, a);
-    launches += 9;
+    launches += 8;
     if (a.n_excl_ent > 0) {
         cell_excl_map_kernel<<<(unsigned int)((a.n_excl_ent + 255) / 256), 256, 0, st>>>(a);
         ++launches;
