@@ -56,7 +56,7 @@ struct GridParams {
     int seg_len;             // cells per segment along x (>= 2 reach + 1)
     int nsx;                 // segments per cell row
     int n_seg;               // ny * nz * nsx
-    int seg_lo, seg_hi;      // the segments of THIS shard (grid_setup_kernel: equal estimated pair work per rank)
+    int seg_lo, seg_hi;      // the segments of THIS shard (grid_setup: equal estimated pair work per rank)
 };
 
 // Cells whose atoms a shard of the cluster path touches: the cells of its segments plus the cells its force windows

@@ -37,7 +37,7 @@
 namespace jme {
 
 constexpr int kClMaxRows = 13;        // rows of the half shell at reach 2
-constexpr int kClMaxSegLen = 12;      // cells per segment (GridParams::seg_len is clamped to this in grid_setup_kernel)
+constexpr int kClMaxSegLen = 12;      // cells per segment (GridParams::seg_len is clamped to this in grid_setup)
 constexpr int kClRowPitch = 16;       // row-table entries per cell
 constexpr int kClBatch = 32;          // clusters staged per batch
 constexpr int kClWarps = 8;           // warps per CTA, one CTA per SM (about 240 registers per thread; 12 warps at 168 registers were measured no faster)
