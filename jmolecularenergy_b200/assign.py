@@ -336,6 +336,78 @@ class Assigner:
             v3 = f32(f32(math.sqrt(float(f32(f32(vj) * f32(vk))))) / f32((gj.crd - 1) * (gk.crd - 1)))
         return v1, v2, v3
 
+    # ---- formal charges: MMFF94.java:404-564
+    _FIXED_FORMAL = {34: 1.0, 49: 1.0, 51: 1.0, 54: 1.0, 58: 1.0, 92: 1.0, 93: 1.0, 94: 1.0, 97: 1.0,
+                     87: 2.0, 95: 2.0, 96: 2.0, 98: 2.0, 99: 2.0, 88: 3.0,
+                     35: -1.0, 62: -1.0, 89: -1.0, 90: -1.0, 91: -1.0}
+
+    def formal_charges(self, input_formal: Optional[Sequence[int]] = None) -> List[float]:
+        """``calculateFormalCharge``: the MMFF formal charge of every atom from its type and surroundings - fixed
+        values for the ionic types, a negative charge shared among the terminal O / S of carboxylates, phosphates,
+        sulfonates ... (types 32, 72: ``:411-468``), among the nitrogens of a tetrazole-like anion ring (76,
+        ``:470-482``), and the integer charges the INPUT carries (``IAtom.getFormalCharge``) averaged over the
+        conjugated nitrogens of amidinium / guanidinium / imidazolium groups (55, 56, 81: ``:483-516``).  An atom counts
+        as aromatic when one of its bonds does."""
+        n = self.n
+        input_formal = [0] * n if input_formal is None else [int(round(float(x))) for x in input_formal]
+        z = [g.atomic_number for g in self.geom]
+        aromatic_atom = [any(self.arom[(a, b)] for b in self.nbrs[a]) for a in range(n)]
+        out = [0.0] * n
+        for a in range(n):
+            ta = self.types[a]
+            if ta in (32, 72):
+                amine2, terminal = 0, 0                       # (running counts over the neighbours, as in the reference)
+                for nb in self.nbrs[a]:
+                    for n2 in self.nbrs[nb]:
+                        if z[n2] == 7 and len(self.nbrs[n2]) == 2 and not aromatic_atom[n2]:
+                            amine2 += 1
+                        elif z[n2] in (8, 16) and len(self.nbrs[n2]) == 1:
+                            terminal += 1
+                    if z[nb] == 16 and terminal == 2 and amine2 == 1:
+                        amine2 = 0                            # sulfonamide
+                    tn = self.types[nb]
+                    if z[nb] == 6 and terminal != 0:
+                        out[a] = -1.0 if terminal == 1 else -(terminal - 1) / float(terminal)
+                        break
+                    if tn == 45 and terminal == 3:
+                        out[a] = -1.0 / 3.0
+                        break
+                    if tn in (25, 73) and terminal != 0:
+                        out[a] = 0.0 if terminal == 1 else -(terminal - 1) / float(terminal)
+                        break
+                    if tn == 18 and terminal != 0:
+                        out[a] = 0.0 if amine2 + terminal == 2 else -(amine2 + terminal - 2) / float(terminal)
+                        break
+                    if tn == 77 and terminal != 0:
+                        out[a] = -1.0 / float(terminal)
+                        break
+            elif ta == 76:
+                if self.rings_of[a]:
+                    ring = self.rings[self.rings_of[a][0]]
+                    out[a] = -1.0 / float(sum(1 for x in ring if self.types[x] == 76))
+            elif ta in (55, 56, 81):
+                group = {a}
+                charge = input_formal[a]
+                grown = True
+                while grown:
+                    grown = False
+                    for x in sorted(group):
+                        for nb in self.nbrs[x]:
+                            if self.types[nb] not in (57, 80):
+                                continue
+                            for n2 in self.nbrs[nb]:
+                                if self.types[n2] in (55, 56, 81) and n2 not in group:
+                                    group.add(n2)
+                                    charge += input_formal[n2]
+                                    grown = True
+                out[a] = charge / float(len(group))
+            elif ta == 61:
+                if any(self.types[nb] == 42 for nb in self.nbrs[a]):
+                    out[a] = 1.0
+            elif ta in self._FIXED_FORMAL:
+                out[a] = self._FIXED_FORMAL[ta]
+        return out
+
     # ---- charges: MMFF94.java:566-618 with ring-aware bond types
     def partial_charges(self, formal: Sequence[float]) -> np.ndarray:
         t = self.t
@@ -374,11 +446,13 @@ class Assigner:
 def assign_parameters(tables: MMFFTables, xyz, types: Sequence[int], bonds: Sequence[Tuple[int, int]],
                       orders: Sequence[int], aromatic: Optional[Sequence[bool]] = None,
                       formal: Optional[Sequence[float]] = None, name: str = "", expected_energy: Optional[float] = None,
-                      source: str = "") -> MolecularSystem:
-    """The flattened result of ``MMFF94.assignParameters`` (``MMFF94.java:111-219``) for given atom types."""
+                      source: str = "", input_formal: Optional[Sequence[int]] = None) -> MolecularSystem:
+    """The flattened result of ``MMFF94.assignParameters`` (``MMFF94.java:111-219``) for given atom types.  ``formal``:
+    MMFF formal charges when the caller has them; otherwise they are derived as the reference does (``formal_charges``)
+    from the types and the integer formal charges of the input structure (``input_formal``, default all zero)."""
     A = Assigner(tables, types, bonds, orders, aromatic)
     n = A.n
-    formal = [0.0] * n if formal is None else [float(f) for f in formal]
+    formal = A.formal_charges(input_formal) if formal is None else [float(f) for f in formal]
     linear = [1 if g.linear else 0 for g in A.geom]
     charges = A.partial_charges(formal)
     bond_kb, bond_r0 = [], []

@@ -50,6 +50,7 @@ MOL2 = f"{REF}/src/test/resources/org/jme/forcefield/mmff/MMFF94_dative.mol2"
 ENERGIES = f"{REF}/src/test/resources/org/jme/forcefield/mmff/MMFF94.energies"
 
 LAST_AROMATIC_BONDS = set()
+LAST_INPUT_FORMAL = []
 WATER = {"O": 70, "H": 31}
 # name -> (type per atom by mol2 atom order | callable(symbol)->type, {atom index: formal charge})
 HAND_TYPED = {
@@ -175,12 +176,33 @@ def auto_types(atoms, bonds, allow_rings=False):
     def top(i):
         return max((o for _, o in nb[i]), default=0)
 
+    def terminal_chalcogens(i):
+        return [j for j, _ in nb[i] if el[j] in ("O", "S") and len(nb[j]) == 1]
+
+    def carboxylate_c(i):                       # CO2M / CS2M: a carbon with two terminal O / S and no acid hydrogen
+        return el[i] == "C" and len(nb[i]) == 3 and len(terminal_chalcogens(i)) == 2
+
+    def cation_n(i):                            # a nitrogen with three neighbours and a double bond that is not a nitro group
+        return el[i] == "N" and len(nb[i]) == 3 and top(i) == 2 and not aromatic_atom[i] and len(terminal_chalcogens(i)) == 0
+
+    def cation_c_nitrogens(i):                  # the nitrogens on a carbon that is double-bonded to a cationic nitrogen, else 0
+        if el[i] != "C" or len(nb[i]) != 3 or not any(o == 2 and cation_n(j) for j, o in nb[i]):
+            return 0
+        return sum(1 for j, _ in nb[i] if el[j] == "N" and len(nb[j]) == 3 and not aromatic_atom[j])
+
+    # integer formal charges as the input structure carries them (the reference reads IAtom.getFormalCharge for the
+    # amidinium / guanidinium / imidazolium sharing rule): +1 on the nitrogen drawn with the double bond
+    input_formal = [0] * n
     t = [0] * n
     for i in range(n):
         e, deg, mo = el[i], len(nb[i]), top(i)
         if e == "C":
             if deg == 4:
                 t[i] = 22 if 3 in ring_sizes[i] else (20 if 4 in ring_sizes[i] else 1)     # CR3R, CR4R, CR
+            elif carboxylate_c(i):
+                t[i] = 41                                                                  # CO2M, CS2M
+            elif cation_c_nitrogens(i) >= 2 and not aromatic_atom[i]:
+                t[i] = 57                                                                  # CNN+, CGD+
             elif deg == 3 and five_role.get(i) in ("A", "B") and not double_to(i, ("O", "S")) \
                     and not any(o == 2 and not aromatic_atom[j] for j, o in nb[i]):
                 t[i] = 63 if five_role[i] == "A" else 64                                   # C5A, C5B
@@ -204,8 +226,12 @@ def auto_types(atoms, bonds, allow_rings=False):
                 t[i] = 70 if all(el[j] == "H" for j, _ in nb[i]) else 6
             elif deg == 1:
                 j, o = nb[i][0]
-                if el[j] == "C" and o == 2:
+                if el[j] == "C" and carboxylate_c(j):
+                    t[i] = 32                                                              # O2CM
+                elif el[j] == "C" and o == 2:
                     t[i] = 7
+                elif el[j] == "C" and o == 1:
+                    t[i] = 35                                                              # OM: alkoxide, phenoxide, enolate
                 elif el[j] == "N":
                     t[i] = 7 if len(nb[j]) == 2 else 32
                 elif el[j] == "S":
@@ -219,6 +245,14 @@ def auto_types(atoms, bonds, allow_rings=False):
                 return None
         elif e == "S":
             t[i] = {(2, 1): 15, (1, 2): 16}.get((deg, mo), {3: 17, 4: 18}.get(deg, 0))
+            if deg == 1:
+                j, o = nb[i][0]
+                if el[j] == "C" and o == 2 and not carboxylate_c(j):
+                    t[i] = 16                                                              # S=C
+                else:
+                    t[i] = 72                                                              # S2CM, SM, terminal S on P / S
+            if deg == 2 and sum(o == 2 for _, o in nb[i]) == 2:
+                t[i] = 74                                                                  # =S=O
             if deg == 2 and five_role.get(i) == "X":
                 t[i] = 44                                                                  # STHI
             if not t[i]:
@@ -249,11 +283,32 @@ def auto_types(atoms, bonds, allow_rings=False):
             if deg == 2:
                 t[i] = 38                                                                  # NPYD
                 continue
+            if deg == 3 and 6 in ring_sizes[i] and i not in five_role:
+                t[i] = 69 if terminal_chalcogens(i) else 58                                # NPOX, NPD+
+                continue
             return None
         if deg == 1 and mo == 3:
             t[i] = 42
+        elif deg == 1 and mo == 2 and el[nb[i][0][0]] == "N":
+            t[i] = 47                                                                      # NAZT
+        elif deg == 2 and sum(o == 2 for _, o in nb[i]) == 2:
+            t[i] = 53                                                                      # =N=
         elif deg == 2 and mo == 2:
             t[i] = 46 if double_to(i, ("O",)) else 9
+        elif deg == 2 and mo == 1 and any(el[j] == "S" and len(nb[j]) == 4 for j, _ in nb[i]):
+            t[i] = 62                                                                      # NM: deprotonated sulfonamide
+        elif deg == 4:
+            t[i] = 68 if terminal_chalcogens(i) else 34                                    # N3OX, NR+
+        elif deg == 3 and mo == 2 and len(terminal_chalcogens(i)) == 1 and double_to(i, ("C", "N")):
+            t[i] = 67                                                                      # N2OX
+        elif cation_n(i):
+            c = [j for j, o in nb[i] if o == 2][0]
+            k = cation_c_nitrogens(c)
+            t[i] = 56 if k == 3 else (55 if k == 2 else 54)                                # NGD+, NCN+, N+=C
+            input_formal[i] = 1
+        elif deg == 3 and mo == 1 and any(cation_c_nitrogens(j) >= 2 for j, _ in nb[i]):
+            c = [j for j, _ in nb[i] if cation_c_nitrogens(j) >= 2][0]
+            t[i] = 56 if cation_c_nitrogens(c) == 3 else 55
         elif deg == 3 and mo == 2:
             t[i] = 45
         elif deg == 3 and mo == 1:
@@ -281,7 +336,8 @@ def auto_types(atoms, bonds, allow_rings=False):
         elif e in ("S", "P"):
             t[i] = 71
         elif e == "N":
-            t[i] = {8: 23, 10: 28, 40: 28, 43: 28, 9: 27, 39: 23}.get(t[j], 0)
+            t[i] = {8: 23, 10: 28, 40: 28, 43: 28, 9: 27, 39: 23, 34: 36, 54: 36, 55: 36, 56: 36, 58: 36, 81: 36,
+                    48: 28, 62: 23, 67: 23, 68: 23}.get(t[j], 0)
         elif e == "O":
             if t[j] == 70:
                 t[i] = 31
@@ -295,8 +351,12 @@ def auto_types(atoms, bonds, allow_rings=False):
                         t[i] = 33
                     elif el[x] == "P":
                         t[i] = 24
+                    else:
+                        t[i] = 21                                                          # HOR: on N-O-H and the rest
         if not t[i]:
             return None
+    global LAST_INPUT_FORMAL
+    LAST_INPUT_FORMAL = input_formal
     return t
 
 
@@ -516,12 +576,14 @@ def pin_suite(tables, mol2_path, energies_path, prefix, hand_typed, kept, tolera
         else:
             types = list(typing)
         formal = [ion_charges.get(a[0], 0.0) for a in m["atoms"]]
+        input_formal = None
         xyz = [[a[1], a[2], a[3]] for a in m["atoms"]]
         bonds = [(a, b) for a, b, _ in m["bonds"]]
         aromatic = [o == "ar" for _, _, o in m["bonds"]]
         if how.startswith("rule"):               # the perception of auto_types (run again: it keeps the last result)
             auto_types(m["atoms"], m["bonds"], allow_rings=True)
             aromatic = [frozenset((a, b)) in LAST_AROMATIC_BONDS for a, b, _ in m["bonds"]]
+            formal, input_formal = None, list(LAST_INPUT_FORMAL)      # derived as the reference does (formal_charges)
         expected, eline = energies[name]
         src = (f"{os.path.basename(mol2_path)}:{m['line']} / {os.path.basename(energies_path)}:{eline} (OPTIMOL); "
                f"{how} types {types}")
@@ -531,7 +593,7 @@ def pin_suite(tables, mol2_path, energies_path, prefix, hand_typed, kept, tolera
         for orders in kekule_variants(len(types), m["bonds"]):
             try:
                 s = assign_parameters(tables, xyz, types, bonds, orders, aromatic, formal, name=prefix + name,
-                                      expected_energy=expected, source=src)
+                                      expected_energy=expected, source=src, input_formal=input_formal)
             except (ParameterNotTabulated, AssignmentError, KeyError) as exc:
                 verdict = f"SKIP {prefix}{name}: {exc}"
                 continue
