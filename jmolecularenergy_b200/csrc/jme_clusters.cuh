@@ -40,7 +40,13 @@ constexpr int kClMaxRows = 13;        // rows of the half shell at reach 2
 constexpr int kClMaxSegLen = 12;      // cells per segment (GridParams::seg_len is clamped to this in grid_setup)
 constexpr int kClRowPitch = 16;       // row-table entries per cell
 constexpr int kClBatch = 32;          // clusters staged per batch
-constexpr int kClWarps = 8;           // warps per CTA, one CTA per SM (about 240 registers per thread; 12 warps at 168 registers were measured no faster)
+#ifndef JME_CL_WARPS
+#define JME_CL_WARPS 8
+#endif
+// warps per CTA, one CTA per SM, 230 registers per thread.  A third warp on any scheduler caps the registers at 168
+// (16 K registers per scheduler): measured on 10^6 ions 9 / 10 warps 1.91 / 1.81 ms against 1.68 ms with 8, and the
+// smaller windows of 10 warps overflow into the atomics
+constexpr int kClWarps = JME_CL_WARPS;
 constexpr int kClMaxRing = 128;       // upper bound of the window slots per neighbour row (11 slot bits: 13 * 128 + 1)
 
 // 64-bit list entry: .x = sorted position of the partner, .y = meta
