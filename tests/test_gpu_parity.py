@@ -282,6 +282,51 @@ def test_two_way_shard_sums_to_unsharded(oracle):
         np.testing.assert_allclose(summed[10:], full[10:], rtol=1e-9, atol=1e-9 * np.abs(full[10:]).max())
 
 
+def test_peer_exchange_single_rank_equals_plain_evaluation(oracle):
+    """The owner-mode exchange over peer memory (include/jme_b200.h: jme_peer_*) with a world of one: push to and pull
+    from the own exported block.  Header and gradient must equal a plain device evaluation bit for bit, step after step
+    (the flags count steps); the multi-rank case is tests/test_multi_gpu.py."""
+    from jmolecularenergy_b200 import systems, _lib
+    from jmolecularenergy_b200.forcefield import _GpuState
+    import torch
+    L = _lib.lib()
+    for s, cutoff, path in ((systems.water_box(100), 0.0, 1), (systems.solvated_chains(3001, chain_fraction=0.3), 8.0, 4)):
+        n = s.n_atoms
+        st = _GpuState(s)
+        st.check(L.jme_set_options(st.h, cutoff, 1.0, 0))
+        st.check(L.jme_set_path(st.h, path))
+        st.check(L.jme_set_stream(st.h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        st.sync_coords(s.xyz)
+        total = C.c_double()
+        st.check(L.jme_energy(st.h, C.byref(total), None))             # sizes the lists of the cutoff path
+        plain = torch.zeros(int(L.jme_eval_out_size(st.h, 1)), dtype=torch.float64, device="cuda")
+        xyz = torch.from_numpy(s.xyz).cuda()
+        st.check(L.jme_set_coords_device(st.h, C.c_void_p(xyz.data_ptr()), n))
+        st.check(L.jme_eval_device(st.h, 1, C.c_void_p(plain.data_ptr())))
+        comm = C.c_void_p()
+        assert L.jme_peer_create(0, 1, n, C.byref(comm)) == 0
+        chunk = int(L.jme_peer_chunk(comm))
+        assert chunk >= n and chunk % 2 == 0
+        handle = (C.c_ubyte * 64)()
+        assert L.jme_peer_handle(comm, handle) == 0
+        assert L.jme_peer_open(comm, handle) == 0                      # a world of one maps nothing
+        own = torch.zeros(3 * chunk, dtype=torch.float64, device="cuda")
+        own[:3 * n] = xyz.reshape(-1)
+        grad = torch.empty(3 * chunk, dtype=torch.float64, device="cuda")
+        head = torch.empty(10, dtype=torch.float64, device="cuda")
+        for _ in range(3):
+            grad.fill_(float("nan"))
+            head.fill_(float("nan"))
+            st.check(L.jme_peer_step(comm, st.h, C.c_void_p(own.data_ptr()), C.c_void_p(grad.data_ptr()), C.c_void_p(head.data_ptr())))
+            torch.cuda.synchronize()
+            assert torch.equal(head, plain[:10])
+            assert torch.equal(grad[:3 * n], plain[10:10 + 3 * n])
+        ref = oracle.evaluate(s, cutoff=cutoff, gradient=False) if n <= 1000 else oracle.fast_evaluate(s, cutoff=cutoff, gradient=False)
+        assert abs(float(head[0].item()) - ref["total"]) <= 1e-10 * max(1.0, abs(ref["total"]))
+        L.jme_peer_destroy(comm)
+        st.close()
+
+
 def test_gradient_descent_minimizer_matches_oracle_driven_loop(oracle):
     """The reference's GradientDescentMinimizer loop (restated in jmolecularenergy_b200/minimizer.py) driven
     by the GPU force field vs the same loop driven by the oracle energy: same accepted energies."""
