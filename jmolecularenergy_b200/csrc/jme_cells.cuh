@@ -53,7 +53,7 @@ struct GridParams {
     float edge_f, inv_edge_f, cut2_pad_f;   // FP32 copies for the per-row culling (margins included)
     // cluster path (jme_clusters.cuh): half shell of neighbour rows and the segment decomposition of the cell rows
     int n_half;              // rows in the half shell: reach * (2 reach + 1) + reach + 1  (13 for reach 2)
-    int seg_len;             // cells per segment along x (>= 2 reach + 1)
+    int seg_len;             // cells per segment along x (>= 2 reach)
     int nsx;                 // segments per cell row
     int n_seg;               // ny * nz * nsx
     int seg_lo, seg_hi;      // the segments of THIS shard (grid_setup: equal estimated pair work per rank)
@@ -206,7 +206,9 @@ __device__ void grid_setup(const double* part, int n_part, double cutoff, int ma
     if (g->reach > 2) g->reach = 2;                               // edge >= cutoff / 2 by construction
     {   // segments of the cell rows for the cluster path: about seg_target of them, at least 2 reach + 1 cells long
         const int rows = g->ny * g->nz;
-        const int lmin = 2 * g->reach + 1;
+        // (a window spans seg_len + 2 reach cells: with seg_len >= 2 reach at most two segments of a row cover a cell,
+        // which is what the two slot colours of the j-side partials and cl_cellmask_kernel assume)
+        const int lmin = 2 * g->reach;
         int nsx = seg_target > 0 ? (seg_target + rows - 1) / rows : 1;
         int len = g->nx / (nsx > 0 ? nsx : 1);
         if (len < lmin) len = lmin;
