@@ -154,29 +154,202 @@ __device__ __forceinline__ void st_cs_if64(bool pred, unsigned long long base, u
 
 constexpr int kClListMinBlocks = 3;   // 85 registers per thread: no spills
 
+// shared-memory scratch of one list-building warp (1 540 bytes)
+struct ClBuildSmem {
+    float2 (*fis)[4];    // [32][4] atom il as (x,x) (y,y) (z,z) -: operands of the packed FP32 test
+    int4* rings;         // [16] ring of row o: {first slot, slots, floor(2^32 / slots), -}
+    int* jbs;            // [16] first candidate of half-shell row o
+    int* cws;            // [16] first position of row o's window for this cell
+    int* p0s;            // [16] ring origin of row o: first position of its window for the SEGMENT
+    int* off;            // [17] exclusive prefix of the candidate counts (virtual candidate index)
+};
+constexpr size_t kClBuildSmemBytes = 32 * 4 * sizeof(float2) + 16 * sizeof(int4) + 3 * 16 * sizeof(int) + 17 * sizeof(int);
+__device__ __forceinline__ ClBuildSmem cl_build_smem(unsigned char* base) {      // base: 16-byte aligned
+    ClBuildSmem S;
+    S.fis = reinterpret_cast<float2 (*)[4]>(base);
+    S.rings = reinterpret_cast<int4*>(base + 1024);
+    S.jbs = reinterpret_cast<int*>(base + 1280);
+    S.cws = S.jbs + 16;
+    S.p0s = S.cws + 16;
+    S.off = S.p0s + 16;
+    return S;
+}
+
+// The lists of the clusters [k0, k1) of cell c, by one warp (called by cl_list_kernel, one launch for all cells, or by the
+// sweeping warp of cl_pair_kernel for the cells of its segment).
 template <int C>
-__global__ void __launch_bounds__(kListThreads, kClListMinBlocks)
-cl_list_kernel(CellArrays A, ClListArgs P) {
+__device__ __forceinline__ void cl_build_cell(const CellArrays& A, const GridParams& g, const ClListArgs& P, int c, int k0, int k1,
+                                              int lane, const ClBuildSmem& SM) {
     using F = ClFmt<C>;
-    __shared__ float2 s_fi[kListWarps][32][4];  // atom il as (x,x) (y,y) (z,z) -: operands of the packed FP32 test
-    __shared__ int s_jb[kListWarps][16];        // first candidate of half-shell row o
-    __shared__ int s_cw[kListWarps][16];        // first position of row o's window for this cell
-    __shared__ int s_p0[kListWarps][16];        // ring origin of row o: first position of its window for the SEGMENT
-    __shared__ int4 s_ring[kListWarps][16];     // ring of row o: {first slot, slots, floor(2^32 / slots), -}
-    __shared__ int s_off[kListWarps][17];       // exclusive prefix of the candidate counts (virtual candidate index)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float2 (*fis)[4] = s_fi[warp];
-    int* jbs = s_jb[warp];
-    int* cws = s_cw[warp];
-    int* p0s = s_p0[warp];
-    int4* rings = s_ring[warp];
-    int* off = s_off[warp];
-    const GridParams g = *A.grid;
+    float2 (*fis)[4] = SM.fis;
+    int* jbs = SM.jbs;
+    int* cws = SM.cws;
+    int* p0s = SM.p0s;
+    int4* rings = SM.rings;
+    int* off = SM.off;
     const unsigned int lt_mask = (1u << lane) - 1u;
     const int H = g.n_half;
     const float4* __restrict__ fxyz = A.fxyz;
     const float qnan = __int_as_float(0x7fc00000);
+    const int c0 = A.start[c];
+    const int cx = c % g.nx, cy = (c / g.nx) % g.ny, cz = c / (g.nx * g.ny);
+    const int xa = cx / g.seg_len * g.seg_len;                   // first cell of the segment that sweeps this cell
+    const int seg = (cz * g.ny + cy) * g.nsx + cx / g.seg_len;
+    const int a_begin = c0 + C * k0, a_end = c0 + C * k1;        // sorted positions of this item's clusters
+    int total;
+    {   // candidate range of half-shell row `lane` and the prefix sums that flatten the <= 13 ranges into one
+        // virtual index space, so that every trip has all its slots filled
+        int jb = 0, len = 0, cw = 0, p0 = 0;
+        if (lane < H) {
+            int dy, dz;
+            cl_row_offset(lane, g.reach, dy, dz);
+            const int y2 = cy + dy, z2 = cz + dz;
+            if (y2 >= 0 && y2 < g.ny && z2 < g.nz) {
+                const int x0 = max(cx - g.reach, 0), x1 = min(cx + g.reach, g.nx - 1);
+                const int row = (z2 * g.ny + y2) * g.nx;
+                cw = A.start[row + x0];
+                p0 = A.start[row + max(xa - g.reach, 0)];
+                // own row: only partners later in the sorted order than the first atom of the first cluster
+                jb = lane == 0 ? a_begin + 1 : cw;
+                len = A.start[row + x1 + 1] - jb;
+            }
+        }
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        total = __shfl_sync(0xffffffffu, incl, 31);
+        __syncwarp();
+        if (lane < 16) {
+            jbs[lane] = jb; cws[lane] = cw; p0s[lane] = p0; off[lane] = incl - len;
+            const unsigned int lay = P.layout[seg * 16 + lane];
+            const int cap = (int)(lay >> 16);
+            rings[lane] = make_int4((int)(lay & 0xffffu), cap, cap > 0 ? (int)(0x100000000ull / (unsigned long long)cap) : 0, 0);
+        }
+        if (lane == 16) off[16] = incl - len;                     // = total for lane >= H (len == 0)
+    }
+    for (int ch = a_begin; ch < a_end; ch += 32) {              // at most 32 atoms (32 / C clusters) at a time
+        const int nc = min(32, a_end - ch);                       // multiple of C
+        const int nq = nc / C;
+        if (ch / C + nq > P.ccap) {                               // more clusters than list storage
+            if (lane == 0) A.flags[3] = 1;
+            break;
+        }
+        __syncwarp();
+        {
+            const float4 f = fxyz[min(ch + lane, a_end - 1)];
+            fis[lane][0] = make_float2(f.x, f.x);
+            fis[lane][1] = make_float2(f.y, f.y);
+            fis[lane][2] = make_float2(f.z, f.z);
+        }
+        int my_cnt = 0;                                           // lane kq holds the list length of cluster ch / C + kq
+        bool beyond = false;                                      // a candidate of this lane lies beyond the ring of its row
+        __syncwarp();
+        unsigned long long rows = reinterpret_cast<unsigned long long>(P.list + (size_t)(ch / C) * P.cap);
+        asm volatile("" : "+l"(rows));                            // keep the base in registers
+        int r[kListK];                                            // row of this lane's k-th virtual index (monotone)
+#pragma unroll
+        for (int k = 0; k < kListK; ++k) r[k] = 0;
+        for (int vb = 0; vb < total; vb += 32 * kListK) {
+            float ax[kListK], ay[kListK], az[kListK];
+            unsigned int meta[kListK];
+            int jj[kListK];
+#pragma unroll
+            for (int k = 0; k < kListK; ++k) {
+                const int vi = vb + 32 * k + lane;
+                const bool valid = vi < total;
+                while (r[k] < 15 && vi >= off[r[k] + 1]) ++r[k];
+                const int j = valid ? jbs[r[k]] + (vi - off[r[k]]) : 0;
+                const float4 a = fxyz[j];
+                ax[k] = valid ? a.x : qnan;                       // NaN never passes the distance test
+                ay[k] = a.y; az[k] = a.z;
+                jj[k] = j;
+                // the partner's slot in the force window of the sweeping warp: ring index counted from the ring
+                // origin of its row; a partner further from the window start than the ring is long is flagged
+                const int4 rg = rings[r[k]];
+                const int slot = rg.x + (rg.y > 0 ? cl_ring_mod(valid ? j - p0s[r[k]] : 0, rg.y, (unsigned int)rg.z) : 0);
+                const bool ovf = valid && j - cws[r[k]] >= rg.y;
+                beyond = beyond || ovf;
+                meta[k] = (unsigned int)slot | ((unsigned int)__float_as_int(a.w) << kMetaTypeShift) | (ovf ? kMetaOvf : 0u);
+            }
+            unsigned long long px[kListK / 2], py[kListK / 2], pz[kListK / 2];
+#pragma unroll
+            for (int k = 0; k < kListK; k += 2) {
+                px[k / 2] = f2_bits(make_float2(ax[k], ax[k + 1]));
+                py[k / 2] = f2_bits(make_float2(ay[k], ay[k + 1]));
+                pz[k / 2] = f2_bits(make_float2(az[k], az[k + 1]));
+                asm volatile("" : "+l"(px[k / 2]), "+l"(py[k / 2]), "+l"(pz[k / 2]));
+            }
+            for (int kq = 0; kq < nq; ++kq) {
+                const int p0 = ch + C * kq;                       // first position of the cluster
+                bool h[kListK];
+#pragma unroll
+                for (int k = 0; k < kListK; ++k) h[k] = false;
+#pragma unroll
+                for (int a = 0; a < C; ++a) {
+                    const float4 fxy = *reinterpret_cast<const float4*>(&fis[C * kq + a][0]);   // (x, x, y, y)
+                    const float2 fzz = fis[C * kq + a][2];
+#pragma unroll
+                    for (int k = 0; k < kListK; k += 2) {
+                        const float2 d2 = dist2_x2(f2_bits(make_float2(fxy.x, fxy.y)), f2_bits(make_float2(fxy.z, fxy.w)),
+                                                   f2_bits(fzz), px[k / 2], py[k / 2], pz[k / 2]);
+                        h[k] = h[k] || d2.x <= g.r2f_max;
+                        h[k + 1] = h[k + 1] || d2.y <= g.r2f_max;
+                    }
+                }
+                unsigned int m[kListK], any = 0;
+#pragma unroll
+                for (int k = 0; k < kListK; ++k) {
+                    h[k] = h[k] && jj[k] > p0;                    // half shell: partners later than the cluster's first atom
+                    m[k] = __ballot_sync(0xffffffffu, h[k]);
+                    any |= m[k];
+                }
+                if (any == 0) continue;
+                const int cnt = __shfl_sync(0xffffffffu, my_cnt, kq);
+                int tot = 0;
+#pragma unroll
+                for (int k = 0; k < kListK; ++k) tot += __popc(m[k]);
+                if (cnt + tot <= P.cap) {
+                    unsigned int o = (unsigned int)(kq * P.cap + cnt);
+#pragma unroll
+                    for (int k = 0; k < kListK; ++k) {
+                        // a partner inside the own cluster: the atoms a >= j - p0 do not come before it in the sorted
+                        // order - their pair bits are set as "excluded", the evaluation needs no order test
+                        const int dj = jj[k] - p0;
+                        const unsigned int own = dj < C ? ((((1u << C) - 1u) >> dj) << dj) << kMetaExclShift : 0u;
+                        st_cs_if64(h[k], rows, o + __popc(m[k] & lt_mask), make_uint2((unsigned int)jj[k], meta[k] | own));
+                        o += __popc(m[k]);
+                    }
+                    if (lane == kq) my_cnt += tot;
+                } else if (lane == 0) {
+                    A.flags[0] = 1;
+                }
+            }
+        }
+        // every list is padded to whole trips (at least one) with dummy entries - the cluster's own first atom,
+        // every pair excluded, the dummy window slot - so that the FP64 kernel loads entries unconditionally; bit 30
+        // of the count: some candidate of this cell lies beyond its ring, the clusters' trips need the atomics
+        const bool cell_ovf = __any_sync(0xffffffffu, beyond);
+        for (int kq = 0; kq < nq; ++kq) {
+            const int cnt = __shfl_sync(0xffffffffu, my_cnt, kq);
+            const int full = min(P.cap, max(F::kSpan, (cnt + F::kSpan - 1) / F::kSpan * F::kSpan));
+            for (int i = cnt + lane; i < full; i += 32)
+                st_cs_if64(true, rows, (unsigned int)(kq * P.cap + i),
+                           make_uint2((unsigned int)(ch + C * kq), (unsigned int)P.pool | F::kAllExcl));
+        }
+        if (lane < nq) P.count[ch / C + lane] = my_cnt | (cell_ovf ? 0x40000000 : 0);
+    }
+}
 
+template <int C>
+__global__ void __launch_bounds__(kListThreads, kClListMinBlocks)
+cl_list_kernel(CellArrays A, ClListArgs P) {
+    __shared__ __align__(16) unsigned char s_build[kListWarps][(kClBuildSmemBytes + 15) / 16 * 16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const ClBuildSmem SM = cl_build_smem(s_build[warp]);
+    const GridParams g = *A.grid;
     const long long s0 = g.seg_lo, s1 = g.seg_hi;
     const int cell0 = cl_seg_first_cell(g, s0), cell1 = cl_seg_first_cell(g, s1);
     const int n_items = (cell1 - cell0) * P.parts;
@@ -186,162 +359,12 @@ cl_list_kernel(CellArrays A, ClListArgs P) {
         w = __shfl_sync(0xffffffffu, w, 0);
         if (w >= n_items) break;
         const int c = cell0 + w / P.parts, part = w % P.parts;
-        const int c0 = A.start[c], c1 = A.start[c + 1];
-        const int nclu = (c1 - c0) / C;
+        const int nclu = (A.start[c + 1] - A.start[c]) / C;
         const int per = (nclu + P.parts - 1) / P.parts;
         const int k0 = part * per, k1 = min(nclu, k0 + per);
         if (k0 >= k1) continue;
-        const int cx = c % g.nx, cy = (c / g.nx) % g.ny, cz = c / (g.nx * g.ny);
-        const int xa = cx / g.seg_len * g.seg_len;                   // first cell of the segment that sweeps this cell
-        const int seg = (cz * g.ny + cy) * g.nsx + cx / g.seg_len;
-        const int a_begin = c0 + C * k0, a_end = c0 + C * k1;        // sorted positions of this item's clusters
-        int total;
-        {   // candidate range of half-shell row `lane` and the prefix sums that flatten the <= 13 ranges into one
-            // virtual index space, so that every trip has all its slots filled
-            int jb = 0, len = 0, cw = 0, p0 = 0;
-            if (lane < H) {
-                int dy, dz;
-                cl_row_offset(lane, g.reach, dy, dz);
-                const int y2 = cy + dy, z2 = cz + dz;
-                if (y2 >= 0 && y2 < g.ny && z2 < g.nz) {
-                    const int x0 = max(cx - g.reach, 0), x1 = min(cx + g.reach, g.nx - 1);
-                    const int row = (z2 * g.ny + y2) * g.nx;
-                    cw = A.start[row + x0];
-                    p0 = A.start[row + max(xa - g.reach, 0)];
-                    // own row: only partners later in the sorted order than the first atom of the first cluster
-                    jb = lane == 0 ? a_begin + 1 : cw;
-                    len = A.start[row + x1 + 1] - jb;
-                }
-            }
-            int incl = len;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            total = __shfl_sync(0xffffffffu, incl, 31);
-            __syncwarp();
-            if (lane < 16) {
-                jbs[lane] = jb; cws[lane] = cw; p0s[lane] = p0; off[lane] = incl - len;
-                const unsigned int lay = P.layout[seg * 16 + lane];
-                const int cap = (int)(lay >> 16);
-                rings[lane] = make_int4((int)(lay & 0xffffu), cap, cap > 0 ? (int)(0x100000000ull / (unsigned long long)cap) : 0, 0);
-            }
-            if (lane == 16) off[16] = incl - len;                     // = total for lane >= H (len == 0)
-        }
-        for (int ch = a_begin; ch < a_end; ch += 32) {              // at most 32 atoms (32 / C clusters) at a time
-            const int nc = min(32, a_end - ch);                       // multiple of C
-            const int nq = nc / C;
-            if (ch / C + nq > P.ccap) {                               // more clusters than list storage
-                if (lane == 0) A.flags[3] = 1;
-                break;
-            }
-            __syncwarp();
-            {
-                const float4 f = fxyz[min(ch + lane, a_end - 1)];
-                fis[lane][0] = make_float2(f.x, f.x);
-                fis[lane][1] = make_float2(f.y, f.y);
-                fis[lane][2] = make_float2(f.z, f.z);
-            }
-            int my_cnt = 0;                                           // lane kq holds the list length of cluster ch / C + kq
-            bool beyond = false;                                      // a candidate of this lane lies beyond the ring of its row
-            __syncwarp();
-            unsigned long long rows = reinterpret_cast<unsigned long long>(P.list + (size_t)(ch / C) * P.cap);
-            asm volatile("" : "+l"(rows));                            // keep the base in registers
-            int r[kListK];                                            // row of this lane's k-th virtual index (monotone)
-#pragma unroll
-            for (int k = 0; k < kListK; ++k) r[k] = 0;
-            for (int vb = 0; vb < total; vb += 32 * kListK) {
-                float ax[kListK], ay[kListK], az[kListK];
-                unsigned int meta[kListK];
-                int jj[kListK];
-#pragma unroll
-                for (int k = 0; k < kListK; ++k) {
-                    const int vi = vb + 32 * k + lane;
-                    const bool valid = vi < total;
-                    while (r[k] < 15 && vi >= off[r[k] + 1]) ++r[k];
-                    const int j = valid ? jbs[r[k]] + (vi - off[r[k]]) : 0;
-                    const float4 a = fxyz[j];
-                    ax[k] = valid ? a.x : qnan;                       // NaN never passes the distance test
-                    ay[k] = a.y; az[k] = a.z;
-                    jj[k] = j;
-                    // the partner's slot in the force window of the sweeping warp: ring index counted from the ring
-                    // origin of its row; a partner further from the window start than the ring is long is flagged
-                    const int4 rg = rings[r[k]];
-                    const int slot = rg.x + (rg.y > 0 ? cl_ring_mod(valid ? j - p0s[r[k]] : 0, rg.y, (unsigned int)rg.z) : 0);
-                    const bool ovf = valid && j - cws[r[k]] >= rg.y;
-                    beyond = beyond || ovf;
-                    meta[k] = (unsigned int)slot | ((unsigned int)__float_as_int(a.w) << kMetaTypeShift) | (ovf ? kMetaOvf : 0u);
-                }
-                unsigned long long px[kListK / 2], py[kListK / 2], pz[kListK / 2];
-#pragma unroll
-                for (int k = 0; k < kListK; k += 2) {
-                    px[k / 2] = f2_bits(make_float2(ax[k], ax[k + 1]));
-                    py[k / 2] = f2_bits(make_float2(ay[k], ay[k + 1]));
-                    pz[k / 2] = f2_bits(make_float2(az[k], az[k + 1]));
-                    asm volatile("" : "+l"(px[k / 2]), "+l"(py[k / 2]), "+l"(pz[k / 2]));
-                }
-                for (int kq = 0; kq < nq; ++kq) {
-                    const int p0 = ch + C * kq;                       // first position of the cluster
-                    bool h[kListK];
-#pragma unroll
-                    for (int k = 0; k < kListK; ++k) h[k] = false;
-#pragma unroll
-                    for (int a = 0; a < C; ++a) {
-                        const float4 fxy = *reinterpret_cast<const float4*>(&fis[C * kq + a][0]);   // (x, x, y, y)
-                        const float2 fzz = fis[C * kq + a][2];
-#pragma unroll
-                        for (int k = 0; k < kListK; k += 2) {
-                            const float2 d2 = dist2_x2(f2_bits(make_float2(fxy.x, fxy.y)), f2_bits(make_float2(fxy.z, fxy.w)),
-                                                       f2_bits(fzz), px[k / 2], py[k / 2], pz[k / 2]);
-                            h[k] = h[k] || d2.x <= g.r2f_max;
-                            h[k + 1] = h[k + 1] || d2.y <= g.r2f_max;
-                        }
-                    }
-                    unsigned int m[kListK], any = 0;
-#pragma unroll
-                    for (int k = 0; k < kListK; ++k) {
-                        h[k] = h[k] && jj[k] > p0;                    // half shell: partners later than the cluster's first atom
-                        m[k] = __ballot_sync(0xffffffffu, h[k]);
-                        any |= m[k];
-                    }
-                    if (any == 0) continue;
-                    const int cnt = __shfl_sync(0xffffffffu, my_cnt, kq);
-                    int tot = 0;
-#pragma unroll
-                    for (int k = 0; k < kListK; ++k) tot += __popc(m[k]);
-                    if (cnt + tot <= P.cap) {
-                        unsigned int o = (unsigned int)(kq * P.cap + cnt);
-#pragma unroll
-                        for (int k = 0; k < kListK; ++k) {
-                            // a partner inside the own cluster: the atoms a >= j - p0 do not come before it in the sorted
-                            // order - their pair bits are set as "excluded", the evaluation needs no order test
-                            const int dj = jj[k] - p0;
-                            const unsigned int own = dj < C ? ((((1u << C) - 1u) >> dj) << dj) << kMetaExclShift : 0u;
-                            st_cs_if64(h[k], rows, o + __popc(m[k] & lt_mask), make_uint2((unsigned int)jj[k], meta[k] | own));
-                            o += __popc(m[k]);
-                        }
-                        if (lane == kq) my_cnt += tot;
-                    } else if (lane == 0) {
-                        A.flags[0] = 1;
-                    }
-                }
-            }
-            // every list is padded to whole trips (at least one) with dummy entries - the cluster's own first atom,
-            // every pair excluded, the dummy window slot - so that the FP64 kernel loads entries unconditionally; bit 30
-            // of the count: some candidate of this cell lies beyond its ring, the clusters' trips need the atomics
-            const bool cell_ovf = __any_sync(0xffffffffu, beyond);
-            for (int kq = 0; kq < nq; ++kq) {
-                const int cnt = __shfl_sync(0xffffffffu, my_cnt, kq);
-                const int full = min(P.cap, max(F::kSpan, (cnt + F::kSpan - 1) / F::kSpan * F::kSpan));
-                for (int i = cnt + lane; i < full; i += 32)
-                    st_cs_if64(true, rows, (unsigned int)(kq * P.cap + i),
-                               make_uint2((unsigned int)(ch + C * kq), (unsigned int)P.pool | F::kAllExcl));
-            }
-            if (lane < nq) P.count[ch / C + lane] = my_cnt | (cell_ovf ? 0x40000000 : 0);
-        }
+        cl_build_cell<C>(A, g, P, c, k0, k1, lane, SM);
     }
-    (void)F::kK;
 }
 
 // ---- exclusion / 1-4 bits ------------------------------------------------------------------------------
