@@ -218,6 +218,14 @@ class ShardedMMFF94:
         self._peer = comm
         return True
 
+    def close_peer_exchange(self) -> None:
+        """Back to the collectives (every rank must do it at the same point of its loop)."""
+        if self._peer is not None:
+            self.torch.cuda.synchronize(self.device)
+            self.dist.barrier()                      # nobody unmaps a block a peer still reads
+            self.L.jme_peer_destroy(self._peer)
+            self._peer = None
+
     def step_owned(self, xyz_own, out_full, grad_own, xyz_full=None) -> None:
         """One owner-mode step: ``xyz_own`` (3 * chunk doubles on this rank's device) in, ``out_full[:10]`` = the
         job-wide header and ``grad_own`` (3 * chunk) out.  Over peer memory when ``open_peer_exchange`` was called,
