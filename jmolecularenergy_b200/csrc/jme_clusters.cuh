@@ -154,24 +154,21 @@ __device__ __forceinline__ void st_cs_if64(bool pred, unsigned long long base, u
 
 constexpr int kClListMinBlocks = 3;   // 85 registers per thread: no spills
 
-// shared-memory scratch of one list-building warp (1 540 bytes)
+// shared-memory scratch of one list-building warp (1 604 bytes)
 struct ClBuildSmem {
     float2 (*fis)[4];    // [32][4] atom il as (x,x) (y,y) (z,z) -: operands of the packed FP32 test
     int4* rings;         // [16] ring of row o: {first slot, slots, floor(2^32 / slots), -}
-    int* jbs;            // [16] first candidate of half-shell row o
-    int* cws;            // [16] first position of row o's window for this cell
-    int* p0s;            // [16] ring origin of row o: first position of its window for the SEGMENT
+    int4* rowa;          // [16] row o: {first candidate - its virtual index, ring origin (first position of the row's window
+                         //      for the SEGMENT), first position of its window for this cell, -}
     int* off;            // [17] exclusive prefix of the candidate counts (virtual candidate index)
 };
-constexpr size_t kClBuildSmemBytes = 32 * 4 * sizeof(float2) + 16 * sizeof(int4) + 3 * 16 * sizeof(int) + 17 * sizeof(int);
+constexpr size_t kClBuildSmemBytes = 32 * 4 * sizeof(float2) + 2 * 16 * sizeof(int4) + 17 * sizeof(int);
 __device__ __forceinline__ ClBuildSmem cl_build_smem(unsigned char* base) {      // base: 16-byte aligned
     ClBuildSmem S;
     S.fis = reinterpret_cast<float2 (*)[4]>(base);
     S.rings = reinterpret_cast<int4*>(base + 1024);
-    S.jbs = reinterpret_cast<int*>(base + 1280);
-    S.cws = S.jbs + 16;
-    S.p0s = S.cws + 16;
-    S.off = S.p0s + 16;
+    S.rowa = reinterpret_cast<int4*>(base + 1280);
+    S.off = reinterpret_cast<int*>(base + 1536);
     return S;
 }
 
@@ -182,9 +179,7 @@ __device__ __forceinline__ void cl_build_cell(const CellArrays& A, const GridPar
                                               int lane, const ClBuildSmem& SM) {
     using F = ClFmt<C>;
     float2 (*fis)[4] = SM.fis;
-    int* jbs = SM.jbs;
-    int* cws = SM.cws;
-    int* p0s = SM.p0s;
+    int4* rowa = SM.rowa;
     int4* rings = SM.rings;
     int* off = SM.off;
     const unsigned int lt_mask = (1u << lane) - 1u;
@@ -223,7 +218,7 @@ __device__ __forceinline__ void cl_build_cell(const CellArrays& A, const GridPar
         total = __shfl_sync(0xffffffffu, incl, 31);
         __syncwarp();
         if (lane < 16) {
-            jbs[lane] = jb; cws[lane] = cw; p0s[lane] = p0; off[lane] = incl - len;
+            rowa[lane] = make_int4(jb - (incl - len), p0, cw, 0); off[lane] = incl - len;
             const unsigned int lay = P.layout[seg * 16 + lane];
             const int cap = (int)(lay >> 16);
             rings[lane] = make_int4((int)(lay & 0xffffu), cap, cap > 0 ? (int)(0x100000000ull / (unsigned long long)cap) : 0, 0);
@@ -249,9 +244,9 @@ __device__ __forceinline__ void cl_build_cell(const CellArrays& A, const GridPar
         __syncwarp();
         unsigned long long rows = reinterpret_cast<unsigned long long>(P.list + (size_t)(ch / C) * P.cap);
         asm volatile("" : "+l"(rows));                            // keep the base in registers
-        int r[kListK];                                            // row of this lane's k-th virtual index (monotone)
-#pragma unroll
-        for (int k = 0; k < kListK; ++k) r[k] = 0;
+        int r[kListK], nxt[kListK];                               // row of this lane's k-th virtual index (monotone) and where
+#pragma unroll                                                    // the next row starts (kept in a register: no table read
+        for (int k = 0; k < kListK; ++k) { r[k] = 0; nxt[k] = off[1]; }   // per trip when no boundary is crossed)
         for (int vb = 0; vb < total; vb += 32 * kListK) {
             float ax[kListK], ay[kListK], az[kListK];
             unsigned int meta[kListK];
@@ -260,8 +255,9 @@ __device__ __forceinline__ void cl_build_cell(const CellArrays& A, const GridPar
             for (int k = 0; k < kListK; ++k) {
                 const int vi = vb + 32 * k + lane;
                 const bool valid = vi < total;
-                while (r[k] < 15 && vi >= off[r[k] + 1]) ++r[k];
-                const int j = valid ? jbs[r[k]] + (vi - off[r[k]]) : 0;
+                while (r[k] < 15 && vi >= nxt[k]) { ++r[k]; nxt[k] = off[r[k] + 1]; }
+                const int4 ra = rowa[r[k]];
+                const int j = valid ? ra.x + vi : 0;
                 const float4 a = fxyz[j];
                 ax[k] = valid ? a.x : qnan;                       // NaN never passes the distance test
                 ay[k] = a.y; az[k] = a.z;
@@ -269,8 +265,8 @@ __device__ __forceinline__ void cl_build_cell(const CellArrays& A, const GridPar
                 // the partner's slot in the force window of the sweeping warp: ring index counted from the ring
                 // origin of its row; a partner further from the window start than the ring is long is flagged
                 const int4 rg = rings[r[k]];
-                const int slot = rg.x + (rg.y > 0 ? cl_ring_mod(valid ? j - p0s[r[k]] : 0, rg.y, (unsigned int)rg.z) : 0);
-                const bool ovf = valid && j - cws[r[k]] >= rg.y;
+                const int slot = rg.x + (rg.y > 0 ? cl_ring_mod(valid ? j - ra.y : 0, rg.y, (unsigned int)rg.z) : 0);
+                const bool ovf = valid && j - ra.z >= rg.y;
                 beyond = beyond || ovf;
                 meta[k] = (unsigned int)slot | ((unsigned int)__float_as_int(a.w) << kMetaTypeShift) | (ovf ? kMetaOvf : 0u);
             }
