@@ -541,10 +541,10 @@ def main():
             base, _, _ = cpu_baseline(args.workload, faithful=False)
             line["cpu_baseline"] = base
         emit(line)
+    ev.close()                       # (collective while the peer exchange is open: before the process group goes)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    ev.close()
 
 
 if __name__ == "__main__":

@@ -250,9 +250,8 @@ class ShardedMMFF94:
         return 0 if self.state is None else int(self.L.jme_launch_count(self.state.h))
 
     def close(self) -> None:
-        if self._peer is not None:
-            self.L.jme_peer_destroy(self._peer)
-            self._peer = None
+        """Collective when the peer exchange is open (a barrier: nobody frees a block that a peer's last pull still reads)."""
+        self.close_peer_exchange()
         if self.state is not None:
             self.state.close()
             self.state = None
