@@ -26,7 +26,8 @@
 //               (coalesced), so a j-atom receives exactly one partial per (row of the half shell, segment) - no
 //               atomics, every partial has one writer and the final sum a fixed order => bit-reproducible.
 //               Entries and partner records travel through registers: entries two trips ahead (their cache lines
-//               are prefetched to L2 a whole cluster ahead), records one trip ahead.
+//               are prefetched to L2 a whole cluster ahead), records one trip ahead.  Lists are padded to whole trips
+//               and the trips of a batch of clusters are numbered through, so the trip loop is one basic block.
 //   cl_reduce   per cell: which of the <= 26 j-side slots were written for it follows from the grid (nothing is
 //               stored); per atom: i-side sum + those slots + bonded slots; unit conversion; scatter to the
 //               caller's atom order.

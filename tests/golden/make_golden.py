@@ -39,7 +39,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
-from jmolecularenergy_b200.assign import AssignmentError, assign_parameters, find_rings   # noqa: E402
+from jmolecularenergy_b200.assign import AssignmentError, assign_parameters   # noqa: E402
+from jmolecularenergy_b200.atom_typing import ALTERNATIVES, kekule_variants, perceive_types   # noqa: E402
 from jmolecularenergy_b200.builder import parameterize            # noqa: E402
 from jmolecularenergy_b200.mmff_tables import MMFFTables, ParameterNotTabulated  # noqa: E402
 from oracle import py_oracle                                     # noqa: E402
@@ -51,9 +52,8 @@ ENERGIES = f"{REF}/src/test/resources/org/jme/forcefield/mmff/MMFF94.energies"
 
 LAST_AROMATIC_BONDS = set()
 LAST_INPUT_FORMAL = []
-# Where the rules cannot tell two MMFF types apart from connectivity alone, pin_suite tries the alternatives in turn and
-# the published energy and charges decide: "" = the first choice of every rule.
-ALTERNATIVES = ("", "nn8", "enamine8", "amide40")
+# Where the rules cannot tell two MMFF types apart from connectivity alone, pin_suite tries the alternatives
+# (atom_typing.ALTERNATIVES) in turn and the published energy and charges decide: "" = the first choice of every rule.
 ALTERNATIVE = ""
 WATER = {"O": 70, "H": 31}
 # name -> (type per atom by mol2 atom order | callable(symbol)->type, {atom index: formal charge})
@@ -97,339 +97,14 @@ HAND_TYPED = {
 
 
 def auto_types(atoms, bonds, allow_rings=False):
-    """MMFF numeric types for an acyclic, neutral molecule from connectivity and bond orders alone, or None when
-    the molecule is outside what these rules cover.  Types (MMFFSYMB): C 1 alkyl / 2 vinylic / 3 C=O, C=N, C=S /
-    4 sp; H 5 on C, Si / 21 alcohol / 24 acid, on P-O / 29 enol / 33 on S-O / 23 amine / 28 amide, enamine,
-    sulfonamide / 27 imine / 71 on S, P / 31 water; O 6 divalent / 7 carbonyl, nitroso, sulfoxide / 32 terminal O
-    on N (nitro), S (sulfone...), P / 70 water; N 8 amine / 9 imine, azo / 10 amide, hydrazone N / 40 enamine /
-    42 nitrile / 43 sulfonamide / 45 nitro / 46 nitroso; S 15 / 16 thiocarbonyl / 17 sulfoxide / 18 sulfone;
-    P 26 / 25; Si 19; halogens 11-14."""
-    n = len(atoms)
-    el = [a[0] for a in atoms]
-    nb = [[] for _ in range(n)]
-    aromatic_atom = [False] * n
-    for a, b, o in bonds:
-        o = "1" if o == "am" else o
-        if o == "ar":                          # an aromatic bond counts as a multiple bond for the rules below
-            aromatic_atom[a] = aromatic_atom[b] = True
-            o = "2"
-        if o not in ("1", "2", "3"):
-            return None
-        nb[a].append((b, int(o)))
-        nb[b].append((a, int(o)))
-    rings = find_rings(n, [(a, b) for a, b, _ in bonds])
-    if rings and not allow_rings:
+    """The package's rule-based typer (``jmolecularenergy_b200/atom_typing.py``) under the current ALTERNATIVE; keeps the
+    perceived aromatic bonds and input formal charges of the last call."""
+    global LAST_AROMATIC_BONDS, LAST_INPUT_FORMAL
+    res = perceive_types(atoms, bonds, allow_rings=allow_rings, alternative=ALTERNATIVE)
+    if res is None:
         return None
-    if len(bonds) < n - 1:                    # not connected
-        return None
-    ring_sizes = [set() for _ in range(n)]
-    for r in rings:
-        for a in r:
-            ring_sizes[a].add(len(r))
-    arom_bonds = {frozenset((a, b)) for a, b, o in bonds if o == "ar"}
-    for r in rings:                           # mol2 "ar" systems other than six-membered rings are left alone
-        ar_in_ring = sum(1 for k in range(len(r)) if frozenset((r[k], r[(k + 1) % len(r)])) in arom_bonds)
-        if ar_in_ring == len(r) and len(r) != 6:
-            return None
-    # Aromaticity from the Kekule structure (the suites write rings with alternating single / double bonds):
-    #  * six-membered rings of C / N in which every atom has a double bond inside the ring or already belongs to an
-    #    aromatic ring (fused benzenoids), iterated to a fixed point;
-    #  * five-membered rings with two ring double bonds and exactly one atom that donates a lone pair (O, S, or N with
-    #    three neighbours): furans, thiophenes, pyrroles, azoles.
-    order_of = {frozenset((a, b)): ("2" if o == "ar" else ("1" if o == "am" else o)) for a, b, o in bonds}
-    ring_bonds = lambda r: [frozenset((r[k], r[(k + 1) % len(r)])) for k in range(len(r))]
-    arom_ring = []
-    changed = True
-    while changed:
-        changed = False
-        for r in rings:
-            if r in arom_ring or len(r) != 6 or any(el[a] not in ("C", "N") for a in r):
-                continue
-            rb = ring_bonds(r)
-            ok = all(any(order_of[b] == "2" and a in b for b in rb) or aromatic_atom[a] for a in r)
-            if ok and all(len(nb[a]) <= 3 for a in r):
-                arom_ring.append(r)
-                for a in r:
-                    aromatic_atom[a] = True
-                arom_bonds.update(rb)
-                changed = True
-    five_role = {}                            # atom -> "X" (lone-pair donor), "A" (alpha to it), "B" (beta)
-    for r in rings:
-        if len(r) != 5:
-            continue
-        rb = ring_bonds(r)
-        donors = [a for a in r if (el[a] in ("O", "S") and len(nb[a]) == 2) or (el[a] == "N" and len(nb[a]) == 3
-                                                                                and all(o == 1 for _, o in nb[a]))]
-        n_dbl = sum(1 for b in rb if order_of[b] == "2")
-        others_sp2 = all(any(o == 2 for _, o in nb[a]) or aromatic_atom[a] for a in r if a not in donors)
-        if len(donors) == 1 and others_sp2 and (n_dbl == 2 or (n_dbl == 1 and any(aromatic_atom[a] for a in r))) \
-                and all(el[a] in ("C", "N", "O", "S") for a in r):
-            x = r.index(donors[0])
-            five_role[r[x]] = "X"
-            for d, role in ((1, "A"), (4, "A"), (2, "B"), (3, "B")):
-                five_role.setdefault(r[(x + d) % 5], role)
-            arom_bonds.update(rb)
-            for a in r:
-                aromatic_atom[a] = True
-    global LAST_AROMATIC_BONDS
-    LAST_AROMATIC_BONDS = arom_bonds
-
-    def double_to(i, els):
-        return any(o == 2 and el[j] in els for j, o in nb[i])
-
-    def top(i):
-        return max((o for _, o in nb[i]), default=0)
-
-    def terminal_chalcogens(i):
-        return [j for j, _ in nb[i] if el[j] in ("O", "S") and len(nb[j]) == 1]
-
-    def carboxylate_c(i):                       # CO2M / CS2M: a carbon with two terminal O / S and no acid hydrogen
-        return el[i] == "C" and len(nb[i]) == 3 and len(terminal_chalcogens(i)) == 2
-
-    def cation_n(i):                            # a nitrogen with three neighbours and a double bond that is not a nitro group
-        return el[i] == "N" and len(nb[i]) == 3 and top(i) == 2 and not aromatic_atom[i] and len(terminal_chalcogens(i)) == 0
-
-    def cation_c_nitrogens(i):                  # the nitrogens on a carbon that is double-bonded to a cationic nitrogen, else 0
-        if el[i] != "C" or len(nb[i]) != 3 or not any(o == 2 and cation_n(j) for j, o in nb[i]):
-            return 0
-        return sum(1 for j, _ in nb[i] if el[j] == "N" and len(nb[j]) == 3 and not aromatic_atom[j])
-
-    # integer formal charges as the input structure carries them (the reference reads IAtom.getFormalCharge for the
-    # amidinium / guanidinium / imidazolium sharing rule): +1 on the nitrogen drawn with the double bond
-    input_formal = [0] * n
-    t = [0] * n
-    for i in range(n):
-        e, deg, mo = el[i], len(nb[i]), top(i)
-        if e == "C":
-            if deg == 4:
-                t[i] = 22 if 3 in ring_sizes[i] else (20 if 4 in ring_sizes[i] else 1)     # CR3R, CR4R, CR
-            elif carboxylate_c(i):
-                t[i] = 41                                                                  # CO2M, CS2M
-            elif cation_c_nitrogens(i) >= 2 and not aromatic_atom[i]:
-                t[i] = 57                                                                  # CNN+, CGD+
-            elif deg == 3 and five_role.get(i) in ("A", "B") and not double_to(i, ("O", "S")) \
-                    and not any(o == 2 and not aromatic_atom[j] for j, o in nb[i]):
-                t[i] = 63 if five_role[i] == "A" else 64                                   # C5A, C5B
-            elif deg == 3 and aromatic_atom[i] and not any(o == 2 and not aromatic_atom[j] for j, o in nb[i]):
-                t[i] = 37                                                                  # CB
-            elif deg == 3 and mo == 2:
-                if double_to(i, ("O", "N", "S")):
-                    t[i] = 3
-                elif 4 in ring_sizes[i] and any(o == 2 and 4 in ring_sizes[j] for j, o in nb[i]):
-                    t[i] = 30                                                              # CE4R
-                else:
-                    t[i] = 2
-            elif deg == 2 and (mo == 3 or sum(o == 2 for _, o in nb[i]) == 2):
-                t[i] = 4
-            else:
-                return None
-        elif e == "O":
-            if deg == 2 and five_role.get(i) == "X":
-                t[i] = 59                                                                  # OFUR
-            elif deg == 2:
-                t[i] = 70 if all(el[j] == "H" for j, _ in nb[i]) else 6
-            elif deg == 1:
-                j, o = nb[i][0]
-                if el[j] == "C" and carboxylate_c(j):
-                    t[i] = 32                                                              # O2CM
-                elif el[j] == "C" and o == 2:
-                    t[i] = 7
-                elif el[j] == "C" and o == 1:
-                    t[i] = 35                                                              # OM: alkoxide, phenoxide, enolate
-                elif el[j] == "N":
-                    t[i] = 7 if len(nb[j]) == 2 else 32
-                elif el[j] == "S":
-                    terminal = sum(1 for k, _ in nb[j] if el[k] == "O" and len(nb[k]) == 1)
-                    t[i] = 7 if ((len(nb[j]) == 3 and terminal == 1) or len(nb[j]) == 2) else 32      # sulfoxide, sulfine
-                elif el[j] == "P":
-                    t[i] = 32
-                else:
-                    return None
-            else:
-                return None
-        elif e == "S":
-            t[i] = {(2, 1): 15, (1, 2): 16}.get((deg, mo), {3: 17, 4: 18}.get(deg, 0))
-            if deg == 1:
-                j, o = nb[i][0]
-                if el[j] == "C" and o == 2 and not carboxylate_c(j):
-                    t[i] = 16                                                              # S=C
-                else:
-                    t[i] = 72                                                              # S2CM, SM, terminal S on P / S
-            if deg == 2 and sum(o == 2 for _, o in nb[i]) == 2:
-                t[i] = 74                                                                  # =S=O
-            if deg == 2 and five_role.get(i) == "X":
-                t[i] = 44                                                                  # STHI
-            if not t[i]:
-                return None
-        elif e == "P":
-            t[i] = {3: 26, 4: 25}.get(deg, 0)
-            if not t[i]:
-                return None
-        elif e == "SI":
-            t[i] = 19
-        elif e in ("F", "CL", "BR", "I"):
-            if deg != 1:
-                return None
-            t[i] = {"F": 11, "CL": 12, "BR": 13, "I": 14}[e]
-        elif e not in ("N", "H"):
-            return None
-    for i in range(n):                           # nitrogen: needs its neighbours' environment
-        if el[i] != "N":
-            continue
-        deg, mo = len(nb[i]), top(i)
-        if aromatic_atom[i]:
-            if five_role.get(i) == "X" and deg == 3:
-                if t[i] != 81:
-                    t[i] = 39                                                              # NPYL (unless an imidazolium partner already claimed it)
-                continue
-            if five_role.get(i) in ("A", "B") and deg == 2:
-                t[i] = 65 if five_role[i] == "A" else 66                                   # N5A, N5B
-                continue
-            if deg == 2:
-                t[i] = 38                                                                  # NPYD
-                continue
-            if deg == 3 and 6 in ring_sizes[i] and i not in five_role:
-                t[i] = 69 if terminal_chalcogens(i) else 58                                # NPOX, NPD+
-                continue
-            if deg == 3 and mo == 2 and five_role.get(i) == "B" and not terminal_chalcogens(i):
-                # imidazolium-type cation: this nitrogen (drawn with the double bond) and the ring's lone-pair nitrogen two
-                # places away become NIM+, the carbon between them CIM+, the ring's other carbons the general C5
-                ring = [r for r in rings if len(r) == 5 and i in r and any(five_role.get(a) == "X" and el[a] == "N" for a in r)]
-                if len(ring) != 1:
-                    return None
-                ring = ring[0]
-                x = [a for a in ring if five_role.get(a) == "X"][0]
-                between = [a for a in ring if el[a] == "C" and any(j == i for j, _ in nb[a]) and any(j == x for j, _ in nb[a])]
-                if len(between) != 1 or len(nb[x]) != 3:
-                    return None
-                t[i] = t[x] = 81                                                           # NIM+
-                t[between[0]] = 80                                                         # CIM+
-                for a in ring:
-                    if el[a] == "C" and a != between[0] and t[a] in (63, 64):
-                        t[a] = 78                                                          # C5
-                input_formal[i] = 1
-                continue
-            return None
-        if deg == 1 and mo == 3:
-            t[i] = 42
-        elif deg == 1 and mo == 2 and el[nb[i][0][0]] == "N":
-            t[i] = 47                                                                      # NAZT
-        elif deg == 2 and sum(o == 2 for _, o in nb[i]) == 2:
-            t[i] = 53                                                                      # =N=
-        elif deg == 2 and mo == 2:
-            t[i] = 46 if double_to(i, ("O",)) else 9
-        elif deg == 2 and mo == 1 and any(el[j] == "S" and len(nb[j]) == 4 for j, _ in nb[i]):
-            t[i] = 62                                                                      # NM: deprotonated sulfonamide
-        elif deg == 4:
-            t[i] = 68 if terminal_chalcogens(i) else 34                                    # N3OX, NR+
-        elif deg == 3 and mo == 2 and len(terminal_chalcogens(i)) == 1 and double_to(i, ("C", "N")):
-            t[i] = 67                                                                      # N2OX
-        elif cation_n(i):
-            c = [j for j, o in nb[i] if o == 2][0]
-            k = cation_c_nitrogens(c)
-            t[i] = 56 if k == 3 else (55 if k == 2 else 54)                                # NGD+, NCN+, N+=C
-            input_formal[i] = 1
-        elif deg == 3 and mo == 1 and any(cation_c_nitrogens(j) >= 2 for j, _ in nb[i]):
-            c = [j for j, _ in nb[i] if cation_c_nitrogens(j) >= 2][0]
-            t[i] = 56 if cation_c_nitrogens(c) == 3 else 55
-        elif deg == 3 and mo == 2:
-            t[i] = 45
-        elif deg == 3 and mo == 1:
-            kind = 8
-            if any(el[j] == "S" and len(nb[j]) == 4 for j, _ in nb[i]):
-                kind = 43                                                                  # NSO2 (also when acylated)
-            elif any(el[j] == "C" and len(nb[j]) == 2 and any(o == 3 and el[k] == "N" for k, o in nb[j]) for j, _ in nb[i]):
-                kind = 43                                                                  # NC%N: on a cyano group
-            elif any(el[j] == "C" and double_to(j, ("O", "S")) for j, _ in nb[i]):
-                kind = 40 if ALTERNATIVE == "amide40" else 10
-            elif any(el[j] == "N" and top(j) == 2 for j, _ in nb[i]):
-                kind = 8 if ALTERNATIVE == "nn8" else 10                                    # N-N=X: NN=C / NN=N, or a plain amine
-            elif any(el[j] == "S" and len(nb[j]) == 4 for j, _ in nb[i]):
-                kind = 43
-            elif any(el[j] == "C" and top(j) >= 2 for j, _ in nb[i]):
-                kind = 8 if ALTERNATIVE == "enamine8" else 40
-            t[i] = kind
-        else:
-            return None
-    for i in range(n):                           # hydrogen: by the atom it sits on
-        if el[i] != "H":
-            continue
-        if len(nb[i]) != 1:
-            return None
-        j = nb[i][0][0]
-        e = el[j]
-        if e in ("C", "SI"):
-            t[i] = 5
-        elif e in ("S", "P"):
-            t[i] = 71
-        elif e == "N":
-            t[i] = {8: 23, 10: 28, 40: 28, 43: 28, 9: 27, 39: 23, 34: 36, 54: 36, 55: 36, 56: 36, 58: 36, 81: 36,
-                    48: 28, 62: 23, 67: 23, 68: 23}.get(t[j], 0)
-        elif e == "O":
-            if t[j] == 70:
-                t[i] = 31
-            else:
-                x = [k for k, _ in nb[j] if k != i]
-                if len(x) == 1:
-                    x = x[0]
-                    if el[x] == "C":
-                        t[i] = 24 if double_to(x, ("O",)) else (29 if t[x] in (2, 3, 37, 30, 63, 64) else 21)
-                    elif el[x] == "S":
-                        t[i] = 33
-                    elif el[x] == "P":
-                        t[i] = 24
-                    else:
-                        t[i] = 21                                                          # HOR: on N-O-H and the rest
-        if not t[i]:
-            return None
-    global LAST_INPUT_FORMAL
-    LAST_INPUT_FORMAL = input_formal
-    return t
-
-
-def kekule_variants(n, bonds):
-    """Bond orders (1 / 2 / 3) with the aromatic ("ar") bonds of the mol2 record resolved: every perfect matching of
-    the aromatic atoms found by backtracking (at most 4 are tried), then all-single as a last resort."""
-    base = [{"1": 1, "2": 2, "3": 3, "am": 1, "ar": 0}[o] for _, _, o in bonds]
-    ar = [k for k, o in enumerate(base) if o == 0]
-    if not ar:
-        return [base]
-    atoms = sorted({x for k in ar for x in bonds[k][:2]})
-    # an aromatic atom that already carries a double bond outside the aromatic system takes no ring double bond
-    taken = {x for a, b, o in bonds if o == "2" for x in (a, b)}
-    need = [a for a in atoms if a not in taken]
-    out = []
-
-    def solve(idx, used, chosen):
-        if len(out) >= 4:
-            return
-        while idx < len(need) and need[idx] in used:
-            idx += 1
-        if idx == len(need):
-            out.append(list(chosen))
-            return
-        a = need[idx]
-        for k in ar:
-            x, y = bonds[k][:2]
-            if a in (x, y):
-                other = y if x == a else x
-                if other not in used and other not in taken:
-                    solve(idx + 1, used | {a, other}, chosen + [k])
-        # (an atom that stays unmatched, e.g. a pyridine-like N in a non-benzenoid system, is allowed last)
-        solve(idx + 1, used | {a}, chosen)
-
-    solve(0, frozenset(), [])
-    variants = []
-    for chosen in out:
-        v = list(base)
-        for k in ar:
-            v[k] = 2 if k in chosen else 1
-        if v not in variants:
-            variants.append(v)
-    v = [1 if o == 0 else o for o in base]
-    if v not in variants:
-        variants.append(v)
-    return variants
+    LAST_AROMATIC_BONDS, LAST_INPUT_FORMAL = res.aromatic_bonds, res.input_formal
+    return res.types
 
 
 def read_mol2(path):
@@ -585,7 +260,7 @@ def write_templates(tables):
     return lines
 
 
-def pin_suite(tables, mol2_path, energies_path, prefix, hand_typed, kept, tolerance, report):
+def pin_suite(tables, mol2_path, energies_path, prefix, hand_typed, kept, tolerance, report, typing_records=None):
     """Type, parameterise and check every record of one validation suite; fixtures that pass are written as
     ``<prefix><name>.json``."""
     mols = read_mol2(mol2_path)
@@ -642,6 +317,11 @@ def pin_suite(tables, mol2_path, energies_path, prefix, hand_typed, kept, tolera
                 if ok and qok:
                     s.save(os.path.join(HERE, f"{prefix}{name}.json"))
                     kept.append(prefix + name)
+                    if typing_records is not None and how.startswith("rule"):
+                        # what tests/test_atom_typing.py feeds the typer with, and what it must answer
+                        typing_records[prefix + name] = {"elements": [a[0] for a in m["atoms"]],
+                                                         "bonds": [[a, b, o] for a, b, o in m["bonds"]],
+                                                         "alternative": alt, "types": list(types)}
                     if diff > 1e-4:
                         tolerance[prefix + name] = 1e-2
                     elif diff > 1e-5:
@@ -657,7 +337,8 @@ def pin_suite(tables, mol2_path, energies_path, prefix, hand_typed, kept, tolera
 def main():
     tables = MMFFTables(PAR_DIR)
     kept, report, tolerance = [], [], {}
-    pin_suite(tables, MOL2, ENERGIES, "", HAND_TYPED, kept, tolerance, report)
+    typing_records = {}
+    pin_suite(tables, MOL2, ENERGIES, "", HAND_TYPED, kept, tolerance, report, typing_records)
     # the MMFF94s suite: same typing, the static out-of-plane / torsion tables (MMFF94.java:265,660)
     pin_suite(MMFFTables(PAR_DIR, mmff94s=True), MOL2.replace("MMFF94_", "MMFF94s_"), ENERGIES.replace("MMFF94.", "MMFF94s."),
               "S_", {}, kept, tolerance, report)
@@ -674,6 +355,9 @@ def main():
                   f"{len(s.tor_i)} torsions")
     with open(os.path.join(HERE, "MANIFEST.json"), "w") as fh:
         json.dump({"pinned": kept, "unpinned": ["ETHANOL"], "tolerance": tolerance}, fh, indent=1)
+        fh.write("\n")
+    with open(os.path.join(HERE, "TYPING.json"), "w") as fh:
+        json.dump(typing_records, fh, separators=(",", ":"))
         fh.write("\n")
     report += write_templates(tables)
     print("\n".join(report))
