@@ -1000,10 +1000,10 @@ inline int cl_configure(CellPlan& p, const DeviceSystem& ds, std::string& err) {
     p.cl_smem_energy = tb + kClWarps * cl_warp_smem(false, (int)pool);
     // segments per resident warp: eight on one GPU (measured on 10^6 ions: segments of 12 / 11 / 8 / 6 / 5 cells give a
     // pair sweep of 1.74 / 1.72 / 1.68 / 1.68 / 1.69 ms - shorter segments balance the warps better, longer ones flush
-    // their windows less often), and four per warp of THIS rank's shard in a multi-GPU job (the shards are 1 / world of
+    // their windows less often), and six per warp of THIS rank's shard in a multi-GPU job (the shards are 1 / world of
     // the segments each: with the single-GPU segment length a rank at N = 4 had 1.6 segments per warp and its pair
-    // kernel ran 45 % over its share)
-    int seg_mult = std::max(8, 4 * std::max(1, p.world));
+    // kernel ran 45 % over its share; measured at N = 2: 8 / 12 / 16 per warp give steps of 1.503 / 1.483 / 1.498 ms)
+    int seg_mult = p.world > 1 ? 6 * p.world : 8;
     if (const char* e = std::getenv("JME_SEG_MULT")) seg_mult = std::max(1, std::atoi(e));      // (development knob)
     p.arr.seg_target = seg_mult * p.sms * kClWarps;
     return JME_OK;
