@@ -214,12 +214,26 @@ def run_opt5k(args):
     dt = time.perf_counter() - t0
     clocks = sampler.stop()
     calls = m.energyCalls
+    # the same loop with every trial move answered by jme_energy_delta (the moved atom's terms only, O(N) per call):
+    # reported beside the headline, which stays the full evaluation per call that the reference's loop makes
+    s2 = build_system("opt5k")
+    ff2 = MMFF94(False)
+    ff2.assignParameters(s2)
+    m2 = NativeGradientDescentMinimizer(ff2, incremental=True)
+    t0 = time.perf_counter()
+    m2.minimize(s2, 1, 0.01, 1e-4)
+    dt2 = time.perf_counter() - t0
+    incremental = {"energy_calls": m2.energyCalls, "energy_calls_per_s": m2.energyCalls / dt2, "us_per_call": 1e6 * dt2 / m2.energyCalls,
+                   "optimizer_steps": m2.step, "energy_first_last": [m2.stepEnergies[0], m2.stepEnergies[-1]],
+                   "final_energy_full_evaluation": ff2.calculateEnergy(s2),
+                   "what": "jme_set_incremental(1): each trial = jme_energy_delta (N - 1 pairs + the atom's bonded terms, old and new position)"}
+    ff2.release(s2)
     line = {"metric": METRIC.replace("energy+forces", "energy only, optimizer loop"), "value": calls * pairs / dt, "unit": UNIT,
             "n_gpus": 1, "steps": calls, "warmup": 0, "ms_per_step": 1e3 * dt / calls, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "opt5k", "description": WORKLOADS["opt5k"]["desc"], "atoms": s.n_atoms, "pairs_per_step": pairs,
                        "energy_calls": calls, "energy_calls_per_s": calls / dt, "optimizer_steps": m.step,
-                       "energy_first_last": [m.stepEnergies[0], m.stepEnergies[-1]]},
+                       "energy_first_last": [m.stepEnergies[0], m.stepEnergies[-1]], "incremental": incremental},
             "e2e": {"value": calls * pairs / dt, "unit": UNIT, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 80},
             "gpu_launches": ff.launchCount(s) - launches0, "clocks": clocks}
     if not args.no_cpu_baseline:

@@ -170,6 +170,17 @@ int jme_adam_minimize(jme_handle_t* h, int max_steps, double step_size, double t
                       double epsilon, double* xyz_inout, int64_t* energy_calls, int* steps_done, double* step_energies,
                       int capacity);
 
+/* The energy CHANGE of a single-coordinate move - what the reference's minimizers compute as the difference of two
+ * full evaluations (GradientDescentMinimizer.java:75-79, AdamMinimizer.java:89-93) - from the terms that contain the
+ * moved atom only: its N - 1 nonbonded pairs (same exclusions, 1-4 scaling, cutoff predicate) and its bonded terms,
+ * each at the old and the new position, with the arithmetic of the full evaluation.  O(N).  Performs the move (like
+ * jme_set_coord1) and returns delta[0] = change of the total, delta[1..7] = change of the seven components, in the
+ * handle's energy unit.  Addition - the reference has nothing like it.
+ * jme_set_incremental(h, 1) makes jme_gd_minimize / jme_adam_minimize use it for every trial move (one full evaluation
+ * at the start only); the default (0) evaluates the full energy per trial like the reference. */
+int jme_energy_delta(jme_handle_t* h, int64_t atom, int axis, double value, double* delta /*[8]*/);
+int jme_set_incremental(jme_handle_t* h, int on);
+
 /* ---- owner-mode exchange of a multi-GPU job over NVLink peer memory ----
  * One process per GPU, every rank owns chunk = jme_peer_chunk() consecutive atoms (by original index; the last
  * ranks' chunks are padded).  Each rank creates a communicator on its current device, hands the 64-byte handle of

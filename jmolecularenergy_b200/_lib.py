@@ -23,7 +23,7 @@ EXPORTS = (
     "jme_measure_fp64_peak", "jme_enumerate_terms", "jme_exclusions", "jme_set_profiling", "jme_profile_read",
     "jme_gd_minimize", "jme_adam_minimize", "jme_active_path",
     "jme_peer_create", "jme_peer_chunk", "jme_peer_handle", "jme_peer_open", "jme_peer_step", "jme_peer_last_error",
-    "jme_peer_destroy",
+    "jme_peer_destroy", "jme_energy_delta", "jme_set_incremental",
 )
 
 _lib = None
@@ -100,6 +100,10 @@ def lib():
                                       c_i32p, c_i64p, c_i32p, c_i64p, c_i32p, c_i64p]
     L.jme_exclusions.restype = C.c_int
     L.jme_exclusions.argtypes = [C.c_int64, C.c_int64, c_i32p, c_i32p, c_i64p, c_i32p, c_u8p, C.c_int64, c_i64p]
+    L.jme_energy_delta.restype = C.c_int
+    L.jme_energy_delta.argtypes = [H, C.c_int64, C.c_int, C.c_double, c_f64p]
+    L.jme_set_incremental.restype = C.c_int
+    L.jme_set_incremental.argtypes = [H, C.c_int]
     L.jme_peer_create.restype = C.c_int
     L.jme_peer_create.argtypes = [C.c_int, C.c_int, C.c_int64, C.POINTER(H)]
     L.jme_peer_chunk.restype = C.c_int64

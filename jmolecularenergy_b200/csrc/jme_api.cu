@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -16,6 +17,7 @@
 #include "jme_cells.cuh"
 #include "jme_clusters.cuh"
 #include "jme_peer.cuh"
+#include "jme_delta.cuh"
 #include "jme_host.hpp"
 #include "jme_kernels.cuh"
 
@@ -85,6 +87,16 @@ struct jme_handle {
     double* h_out = nullptr;   // pinned, mapped header: reduce_kernel writes the results straight into it
     double* h_out_dev = nullptr;   // device alias of h_out
     uint64_t last_pairs = 0, last_cand = 0;
+
+    // single-coordinate energy differences (jme_delta.cuh)
+    long long* d_dx_excl_ptr = nullptr;
+    unsigned int* d_dx_excl_ent = nullptr;
+    double* d_delta_part = nullptr;
+    unsigned int* d_delta_ctr = nullptr;
+    double* h_delta = nullptr;     // pinned, mapped: [0] total, [1..7] components, [8] sequence number
+    double* h_delta_dev = nullptr;
+    uint64_t delta_seq = 0;
+    bool incremental = false;      // the native minimizer loops use jme_energy_delta instead of full evaluations
 
     // CUDA graphs of the all-pairs evaluation sequence {nonbonded | bonded} -> reduce (launch-bound small
     // systems): one per (gradient?, output buffer); rebuilt whenever anything baked into the kernel arguments changes
@@ -699,6 +711,7 @@ void jme_destroy(jme_handle_t* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->h_delta) cudaFreeHost(h->h_delta);
     delete h;
 }
 
@@ -814,6 +827,81 @@ int jme_energy_gradient(jme_handle_t* h, double* total, double comps[JME_N_COMPO
     return eval_host(h, true, total, comps, grad_xyz);
 }
 
+// The change of the seven components ([1..7]) and of the total ([0]) that moving ONE coordinate causes, and the move
+// itself (jme_delta.cuh): O(N) work.  delta: 8 doubles in the handle's energy unit.
+namespace {
+struct PendingUndo { int64_t atom = -1; int axis = 0; double value = 0; };
+int energy_delta_impl(jme_handle_t* h, int64_t atom, int axis, double value, double* delta, const PendingUndo* undo);
+}  // namespace
+
+int jme_energy_delta(jme_handle_t* h, int64_t atom, int axis, double value, double* delta) {
+    return energy_delta_impl(h, atom, axis, value, delta, nullptr);
+}
+
+namespace {
+int energy_delta_impl(jme_handle_t* h, int64_t atom, int axis, double value, double* delta, const PendingUndo* undo) {
+    if (!h || !delta) return JME_ERR_INVALID;
+    if (atom < 0 || atom >= h->hs.n || axis < 0 || axis > 2) return fail(h, JME_ERR_INVALID, "atom or axis out of range");
+    if (!h->coords_set) return fail(h, JME_ERR_NOT_ASSIGNED, "set all coordinates once before moving single ones");
+    if (h->world != 1) return fail(h, JME_ERR_UNSUPPORTED, "jme_energy_delta on a sharded handle");
+    JME_CUDA(h, cudaSetDevice(h->device));
+    int rc = ensure_plan(h);                       // cutoff threshold, dielectric scale
+    if (rc) return rc;
+    if (!h->h_delta) {
+        std::vector<long long> ptr(h->hs.excl_ptr.begin(), h->hs.excl_ptr.end());
+        std::vector<unsigned int> ent(h->hs.excl_ent.begin(), h->hs.excl_ent.end());
+        if ((rc = dev_upload(h, &h->d_dx_excl_ptr, ptr))) return rc;
+        if ((rc = dev_upload(h, &h->d_dx_excl_ent, ent))) return rc;
+        if ((rc = dev_alloc(h, &h->d_delta_part, 2 * (size_t)kDeltaMaxBlocks))) return rc;
+        if ((rc = dev_alloc(h, &h->d_delta_ctr, 1))) return rc;
+        JME_CUDA(h, cudaMemset(h->d_delta_ctr, 0, sizeof(unsigned int)));
+        if (cudaHostAlloc(&h->h_delta, 16 * sizeof(double), cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer(&h->h_delta_dev, h->h_delta, 0) != cudaSuccess)
+            return fail(h, JME_ERR_CUDA, "cudaHostAlloc (mapped) failed");
+        h->h_delta[8] = 0.0;
+    }
+    DeltaArgs A{};
+    A.S = h->ds;
+    A.x = h->d_x; A.y = h->d_y; A.z = h->d_z;
+    A.atom = (int)atom; A.axis = axis; A.value = value;
+    A.r_atom = undo && undo->atom >= 0 ? (int)undo->atom : -1;
+    A.r_axis = undo ? undo->axis : 0;
+    A.r_value = undo ? undo->value : 0.0;
+    A.cutoff_on = h->cutoff > 0 ? 1 : 0;
+    A.excl_ptr = h->d_dx_excl_ptr; A.excl_ent = h->d_dx_excl_ent;
+    A.B = h->bt; A.slot_ptr = h->d_slot_ptr; A.slot_idx = h->d_slot_idx;
+    A.part = h->d_delta_part; A.done_ctr = h->d_delta_ctr;
+    A.unit_num = h->unit == JME_KCAL_PER_MOL ? 1.0 : kUnitToJoule[JME_KCAL_PER_MOL];
+    A.unit_den = h->unit == JME_KCAL_PER_MOL ? 1.0 : kUnitToJoule[h->unit];
+    A.out_host = h->h_delta_dev;
+    A.seq = (double)(++h->delta_seq);
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(kDeltaMaxBlocks, (h->hs.n + kDeltaThreads - 1) / kDeltaThreads));
+    delta_kernel<<<blocks, kDeltaThreads, 0, h->stream>>>(A);
+    ++h->launches;
+    JME_CUDA(h, cudaGetLastError());
+    h->cells.coords_changed();
+    // the result arrives in mapped host memory, its sequence number last: poll it (a stream synchronisation costs more
+    // than the kernel); give up after two seconds and let the synchronisation report what happened
+    volatile double* flag = h->h_delta + 8;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned spin = 0; *flag != A.seq; ++spin) {
+        if ((spin & 0xfff) == 0xfff && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(2)) {
+            JME_CUDA(h, cudaStreamSynchronize(h->stream));
+            break;
+        }
+    }
+    if (*flag != A.seq) return fail(h, JME_ERR_CUDA, "jme_energy_delta: result not written");
+    for (int c = 0; c < 8; ++c) delta[c] = h->h_delta[c];
+    return JME_OK;
+}
+}  // namespace
+
+int jme_set_incremental(jme_handle_t* h, int on) {
+    if (!h) return JME_ERR_INVALID;
+    h->incremental = on != 0;
+    return JME_OK;
+}
+
 int jme_gd_minimize(jme_handle_t* h, int max_steps, double step_size, double threshold, double* xyz,
                     int64_t* energy_calls, int* steps_done, double* step_energies, int capacity) {
     if (!h || !xyz) return JME_ERR_INVALID;
@@ -826,9 +914,17 @@ int jme_gd_minimize(jme_handle_t* h, int max_steps, double step_size, double thr
         ++calls;
         return eval_host(h, false, &e, nullptr, nullptr);
     };
+    PendingUndo undo;                                              // incremental mode: the undo of a rejected move rides on the next trial
     auto move = [&](int64_t a, int i, double d) -> int {          // movePoint, GradientDescentMinimizer.java:107-115
         xyz[3 * a + i] += d;
+        if (h->incremental) { undo.atom = a; undo.axis = i; undo.value = xyz[3 * a + i]; return JME_OK; }
         return jme_set_coord1(h, a, i, xyz[3 * a + i]);
+    };
+    auto flush_undo = [&]() -> int {
+        if (undo.atom < 0) return JME_OK;
+        const int r = jme_set_coord1(h, undo.atom, undo.axis, undo.value);
+        undo.atom = -1;
+        return r;
     };
     int step = 0;
     std::vector<double> grads(3 * (size_t)n, step_size);           // :51-54
@@ -846,10 +942,20 @@ int jme_gd_minimize(jme_handle_t* h, int max_steps, double step_size, double thr
                 if (g == 0) continue;
                 const double mag = std::min(std::fabs(step_size * g), .3);
                 const double distance = mag * ((g > 0) - (g < 0));             // Math.signum
-                if ((rc = move(a, i, distance))) return rc;
-                double e;
-                if ((rc = energy(e))) return rc;
-                const double difference = e - last_energy;                       // :78
+                double difference;
+                if (h->incremental) {                                            // the move and its energy change in one call
+                    double d8[8];
+                    xyz[3 * a + i] += distance;
+                    ++calls;
+                    if ((rc = energy_delta_impl(h, a, i, xyz[3 * a + i], d8, &undo))) return rc;
+                    undo.atom = -1;
+                    difference = d8[0];
+                } else {
+                    if ((rc = move(a, i, distance))) return rc;
+                    double e;
+                    if ((rc = energy(e))) return rc;
+                    difference = e - last_energy;                                // :78
+                }
                 g = -difference / (distance == 0 ? 1 : distance);               // :79
                 if (!initialized) {
                     if ((rc = move(a, i, -distance))) return rc;
@@ -868,6 +974,7 @@ int jme_gd_minimize(jme_handle_t* h, int max_steps, double step_size, double thr
             if (step_energies && n_log < capacity) step_energies[n_log++] = last_energy;
         }
     }
+    if ((rc = flush_undo())) return rc;
     if (energy_calls) *energy_calls = calls;
     if (steps_done) *steps_done = step;
     return JME_OK;
@@ -885,9 +992,17 @@ int jme_adam_minimize(jme_handle_t* h, int max_steps, double step_size, double t
         ++calls;
         return eval_host(h, false, &e, nullptr, nullptr);
     };
+    PendingUndo undo;                                              // incremental mode: see jme_gd_minimize
     auto move = [&](int64_t a, int i, double d) -> int {          // movePoint, AdamMinimizer.java:122-130
         xyz[3 * a + i] += d;
+        if (h->incremental) { undo.atom = a; undo.axis = i; undo.value = xyz[3 * a + i]; return JME_OK; }
         return jme_set_coord1(h, a, i, xyz[3 * a + i]);
+    };
+    auto flush_undo = [&]() -> int {
+        if (undo.atom < 0) return JME_OK;
+        const int r = jme_set_coord1(h, undo.atom, undo.axis, undo.value);
+        undo.atom = -1;
+        return r;
     };
     struct Adam { double m = 0, v = 0; int t = 1; };              // AdamOptimizer, :132-161
     std::vector<Adam> adams(3 * (size_t)n);
@@ -905,8 +1020,9 @@ int jme_adam_minimize(jme_handle_t* h, int max_steps, double step_size, double t
             for (int i = 0; i < 3; ++i) {
                 double& g = grads[3 * a + i];
                 if (g == 0) continue;                              // :86-88
-                double initial;
-                if ((rc = energy(initial))) return rc;             // :89
+                double initial = 0;
+                if (h->incremental) ++calls;                       // (the energy before the move is the running one)
+                else if ((rc = energy(initial))) return rc;        // :89
                 Adam& o = adams[3 * a + i];
                 const double x = xyz[3 * a + i];
                 ++o.t;                                             // optimize(), :153-160
@@ -915,10 +1031,20 @@ int jme_adam_minimize(jme_handle_t* h, int max_steps, double step_size, double t
                 const double m_hat = o.m / (1 - std::pow(beta1, o.t));
                 const double v_hat = o.v / (1 - std::pow(beta2, o.t));
                 const double distance = (x - step_size * m_hat / (std::sqrt(v_hat) + epsilon)) - x;   // :90
-                if ((rc = move(a, i, distance))) return rc;
-                double e;
-                if ((rc = energy(e))) return rc;
-                const double difference = e - initial;             // :93
+                double difference;
+                if (h->incremental) {
+                    double d8[8];
+                    xyz[3 * a + i] += distance;
+                    ++calls;
+                    if ((rc = energy_delta_impl(h, a, i, xyz[3 * a + i], d8, &undo))) return rc;
+                    undo.atom = -1;
+                    difference = d8[0];
+                } else {
+                    if ((rc = move(a, i, distance))) return rc;
+                    double e;
+                    if ((rc = energy(e))) return rc;
+                    difference = e - initial;                      // :93
+                }
                 g = -difference / std::fabs(distance);             // :94 (a zero step gives +-inf / NaN, like Java)
                 if (!initialized || difference > 0) {
                     if ((rc = move(a, i, -distance))) return rc;   // :95-99
@@ -933,6 +1059,7 @@ int jme_adam_minimize(jme_handle_t* h, int max_steps, double step_size, double t
             if (step_energies && n_log < capacity) step_energies[n_log++] = last_energy;
         }
     }
+    if ((rc = flush_undo())) return rc;
     if (energy_calls) *energy_calls = calls;
     if (steps_done) *steps_done = step;
     return JME_OK;

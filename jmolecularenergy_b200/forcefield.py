@@ -277,6 +277,24 @@ class MMFF94(ForceField):
     def calculateComponents(self, atomContainer: MolecularSystem, gradient: bool = False) -> Dict[str, object]:
         return dict(self._evaluate(atomContainer, gradient=gradient))
 
+    def energyChangeOfMove(self, atomContainer: MolecularSystem, atom: int, axis: int, value: float) -> Dict[str, float]:
+        """Move one coordinate of one atom to ``value`` and return what that changes: ``total`` and the seven components
+        (``jme_energy_delta``: only the moved atom's pairs and bonded terms are evaluated, O(N)).  The container's
+        coordinate is updated too.  No counterpart in the reference, whose minimizers take the difference of two full
+        evaluations."""
+        st = self._state(atomContainer)
+        st.sync_options(self, self.path)
+        st.sync_coords(atomContainer.xyz)
+        d = (C.c_double * 8)()
+        st.check(st.L.jme_energy_delta(st.h, int(atom), int(axis), float(value), d))
+        atomContainer.xyz[atom, axis] = value
+        if st.shadow is not None:
+            st.shadow[3 * atom + axis] = value
+        out = {"total": d[0]}
+        for k, name in enumerate(COMPONENTS):
+            out[name] = d[1 + k]
+        return out
+
     def pairList(self, atomContainer: MolecularSystem):
         """Selected nonbonded pair set (i<j, is14) of the current coordinates and options - diagnostic
         twin of the reference's ``mmff.nonBondedInteraction`` map after the cutoff test."""

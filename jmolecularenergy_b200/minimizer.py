@@ -102,11 +102,14 @@ class GradientDescentMinimizer(EnergyMinimizer):
 class NativeGradientDescentMinimizer(EnergyMinimizer):
     """The same loop as :class:`GradientDescentMinimizer`, run inside ``libjme_b200.so`` (``jme_gd_minimize``): no
     per-call Python / ctypes overhead, which is what BASELINE config 4 (energy calls per second inside the
-    optimizer) measures.  Constraints are not supported on this path."""
+    optimizer) measures.  Constraints are not supported on this path.  ``incremental=True``: every trial move is
+    answered by ``jme_energy_delta`` (the energy change from the moved atom's terms only, O(N)) instead of a full
+    evaluation - same loop, same decisions up to the rounding of the differences."""
 
-    def __init__(self, forcefield):
+    def __init__(self, forcefield, incremental: bool = False):
         super().__init__()
         self.forcefield = forcefield
+        self.incremental = bool(incremental)
         self.energyCalls = 0
         self.stepEnergies = []
 
@@ -119,6 +122,7 @@ class NativeGradientDescentMinimizer(EnergyMinimizer):
         xyz = np.ascontiguousarray(container.xyz, dtype=np.float64)
         calls, steps = C.c_int64(), C.c_int()
         log = np.zeros(maximumSteps + 2)
+        st.check(st.L.jme_set_incremental(st.h, 1 if self.incremental else 0))
         st.check(st.L.jme_gd_minimize(st.h, int(maximumSteps), float(stepSize), float(threshold),
                                       xyz.ctypes.data_as(C.POINTER(C.c_double)), C.byref(calls), C.byref(steps),
                                       log.ctypes.data_as(C.POINTER(C.c_double)), log.shape[0]))
@@ -153,10 +157,11 @@ class _AdamOptimizer:
 class AdamMinimizer(EnergyMinimizer):
     """``AdamMinimizer.minimize`` (``AdamMinimizer.java:62-120``): two energy calls per coordinate."""
 
-    def __init__(self, forceField, beta1: float, beta2: float, epsilon: float):
+    def __init__(self, forceField, beta1: float, beta2: float, epsilon: float, incremental: bool = False):
         super().__init__()
         self.forcefield = forceField
         self.beta1, self.beta2, self.epsilon = beta1, beta2, epsilon
+        self.incremental = bool(incremental)          # see NativeGradientDescentMinimizer
         self.energyCalls = 0
 
     def _energy(self, container) -> float:
@@ -211,10 +216,11 @@ class AdamMinimizer(EnergyMinimizer):
 class NativeAdamMinimizer(EnergyMinimizer):
     """:class:`AdamMinimizer`'s loop run inside ``libjme_b200.so`` (``jme_adam_minimize``); no constraints."""
 
-    def __init__(self, forceField, beta1: float, beta2: float, epsilon: float):
+    def __init__(self, forceField, beta1: float, beta2: float, epsilon: float, incremental: bool = False):
         super().__init__()
         self.forcefield = forceField
         self.beta1, self.beta2, self.epsilon = beta1, beta2, epsilon
+        self.incremental = bool(incremental)          # see NativeGradientDescentMinimizer
         self.energyCalls = 0
         self.stepEnergies = []
 
@@ -227,6 +233,7 @@ class NativeAdamMinimizer(EnergyMinimizer):
         xyz = np.ascontiguousarray(container.xyz, dtype=np.float64)
         calls, steps = C.c_int64(), C.c_int()
         log = np.zeros(maximumSteps + 2)
+        st.check(st.L.jme_set_incremental(st.h, 1 if self.incremental else 0))
         st.check(st.L.jme_adam_minimize(st.h, int(maximumSteps), float(stepSize), float(threshold), float(self.beta1),
                                         float(self.beta2), float(self.epsilon), xyz.ctypes.data_as(C.POINTER(C.c_double)),
                                         C.byref(calls), C.byref(steps), log.ctypes.data_as(C.POINTER(C.c_double)),

@@ -327,6 +327,68 @@ def test_peer_exchange_single_rank_equals_plain_evaluation(oracle):
         st.close()
 
 
+def test_energy_delta_equals_difference_of_full_evaluations(oracle):
+    """``jme_energy_delta`` (the energy change of a single-coordinate move from the moved atom's terms only) against the
+    difference of two full evaluations - the quantity the reference's minimizers compute - per component: molecules with
+    every bonded term type and ions (golden fixtures), a water box without and with a cutoff, other units / dielectric.
+    The oracle's full energy after the moves pins the accumulated result."""
+    from jmolecularenergy_b200 import MMFF94, EnergyUnit, systems
+    rng = np.random.default_rng(11)
+    cases = [(load_golden(n), 0.0) for n in ("ETHANOL", "CO08A", "KHDFRM11", "GUANCH01", "CUVFOO", "ARGIND11") if n in set(golden_names(pinned_only=False))]
+    cases += [(systems.water_box(60), 0.0), (systems.water_box(60), 6.0), (systems.solvated_chains(900, chain_fraction=0.4), 7.5)]
+    assert len(cases) >= 6
+    for s, cutoff in cases:
+        s = s.copy() if hasattr(s, "copy") else s
+        for unit, eps in ((EnergyUnit.KCAL_PER_MOL, 1.0), (EnergyUnit.KJ_PER_MOL, 2.5)):
+            ff = MMFF94(False)
+            ff.setCutoffDistance(cutoff)
+            ff.setDielectricConstant(eps)
+            ff.setEnergyUnit(unit)
+            ff.assignParameters(s)
+            before = ff.calculateComponents(s)
+            running = dict(before)
+            for _ in range(12):
+                a, ax = int(rng.integers(s.n_atoms)), int(rng.integers(3))
+                value = float(s.xyz[a, ax] + rng.uniform(-0.25, 0.25))
+                d = ff.energyChangeOfMove(s, a, ax, value)
+                after = ff.calculateComponents(s)                 # full evaluation of the moved geometry
+                scale = max(1.0, abs(after["total"]))
+                for k in ("total", "bond", "angle", "stretch_bend", "oop", "torsion", "vdw", "ele"):
+                    assert abs(d[k] - (after[k] - before[k])) <= 2e-10 * scale, (s.name, cutoff, k, d[k], after[k] - before[k])
+                    running[k] += d[k]
+                before = after
+            assert abs(running["total"] - before["total"]) <= 1e-9 * max(1.0, abs(before["total"]))
+            if unit == EnergyUnit.KCAL_PER_MOL:
+                ref = oracle.evaluate(s, cutoff=cutoff, dielectric=eps, gradient=False)
+                assert abs(before["total"] - ref["total"]) <= 1e-10 * max(1.0, abs(ref["total"]))
+            ff.release(s)
+
+
+def test_incremental_minimizers_follow_the_full_evaluation_loops():
+    """The native minimizer loops with ``incremental=True`` (every trial answered by jme_energy_delta) against the same
+    loops with a full evaluation per trial: same number of steps and energy calls, step energies equal to rounding."""
+    from jmolecularenergy_b200 import MMFF94, NativeAdamMinimizer, NativeGradientDescentMinimizer, systems
+    for make in (lambda ff, inc: NativeGradientDescentMinimizer(ff, incremental=inc),
+                 lambda ff, inc: NativeAdamMinimizer(ff, 0.9, 0.999, 1e-8, incremental=inc)):
+        runs = []
+        for inc in (False, True):
+            s = systems.water_box(8)
+            s.xyz += np.random.default_rng(5).normal(0, 0.05, s.xyz.shape)
+            ff = MMFF94(False)
+            ff.assignParameters(s)
+            m = make(ff, inc)
+            m.minimize(s, 4, 0.02, 1e-9)
+            final = ff.calculateEnergy(s)
+            runs.append((m.getStep() if hasattr(m, "getStep") else m.step, m.energyCalls, list(m.stepEnergies), final, s.xyz.copy()))
+            ff.release(s)
+        (st0, c0, e0, f0, x0), (st1, c1, e1, f1, x1) = runs
+        assert st0 == st1 and len(e0) == len(e1)
+        assert abs(c0 - c1) <= 1                                   # (the incremental loop makes one full evaluation, at the start)
+        np.testing.assert_allclose(e1, e0, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(x1, x0, rtol=0, atol=1e-9)
+        assert abs(e1[-1] - f1) <= 1e-8 * max(1.0, abs(f1))       # the running energy of the incremental loop is the real one
+
+
 def test_gradient_descent_minimizer_matches_oracle_driven_loop(oracle):
     """The reference's GradientDescentMinimizer loop (restated in jmolecularenergy_b200/minimizer.py) driven
     by the GPU force field vs the same loop driven by the oracle energy: same accepted energies."""
