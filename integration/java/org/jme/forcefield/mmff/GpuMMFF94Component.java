@@ -39,6 +39,7 @@ public final class GpuMMFF94Component extends EnergyComponent implements AutoClo
     private static final MethodHandle COORD1 = h("jme_set_coord1", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, JAVA_INT, JAVA_DOUBLE));
     private static final MethodHandle ENERGY = h("jme_energy", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
     private static final MethodHandle GRADIENT = h("jme_energy_gradient", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle DELTA = h("jme_energy_delta", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, JAVA_INT, JAVA_DOUBLE, ADDRESS));
     private static final MethodHandle LASTERR = h("jme_last_error", FunctionDescriptor.of(ADDRESS, ADDRESS));
     private static final MethodHandle CREATEERR = h("jme_last_create_error", FunctionDescriptor.of(ADDRESS));
 
@@ -47,7 +48,18 @@ public final class GpuMMFF94Component extends EnergyComponent implements AutoClo
     private IAtomContainer bound;          // container the handle was created for
     private Object boundPairMap;           // identity of "mmff.nonBondedInteraction": a new map on every assignParameters
     private double[] shadow;               // coordinates last uploaded (to find the single moved coordinate)
-    private MemorySegment xyz, total, comps;
+    private MemorySegment xyz, total, comps, delta;
+    private boolean incremental;           // opt-in: see setIncremental
+    private double cachedTotal;            // energy of the coordinates in `shadow` (valid while cachedOptions match)
+    private Object cachedOptions;
+    private int sinceFull;
+
+    /** Opt in to incremental energies: when one coordinate changed since the last calculateEnergy - or two: the undo of a
+     *  rejected trial plus the next trial, which is what GradientDescentMinimizer.java:83-93 / AdamMinimizer.java:95-108
+     *  leave between two calls - the answer is the previous energy plus jme_energy_delta (the moved atom's terms only,
+     *  O(N)); every 3 N such answers, and whenever anything else changed, a full evaluation resynchronises.  The
+     *  unmodified minimizers get the speed-up through the unmodified calculateEnergy. */
+    public void setIncremental(boolean on) { incremental = on; }
 
     /** Install on an MMFF94 instance: the seven CPU components out, this one in. */
     public static GpuMMFF94Component install(MMFF94 ff) {
@@ -66,9 +78,40 @@ public final class GpuMMFF94Component extends EnergyComponent implements AutoClo
         if (mol != bound || pairMap != boundPairMap) marshal(mol, pairMap);   // (re)assignParameters happened
         check((int) invoke(OPTIONS, handle, forceField.getCutoffDistance(), forceField.getDielectricConstant(),
                 forceField.getEnergyUnit().ordinal()));                       // KCAL, KJ, JOULE = 0, 1, 2
+        Object options = java.util.List.of(forceField.getCutoffDistance(), forceField.getDielectricConstant(), forceField.getEnergyUnit());
+        if (incremental && shadow != null && options.equals(cachedOptions) && sinceFull < 3 * mol.getAtomCount()) {
+            int n = mol.getAtomCount(), changed = 0;
+            int[] which = new int[2];
+            double[] now = coordinatesOf(mol);
+            for (int k = 0; k < 3 * n && changed <= 2; k++) if (now[k] != shadow[k]) { if (changed < 2) which[changed] = k; changed++; }
+            if (changed == 0) return cachedTotal;
+            if (changed <= 2) {
+                for (int c = 0; c < changed; c++) {
+                    int k = which[c];
+                    check((int) invoke(DELTA, handle, (long) (k / 3), k % 3, now[k], delta));
+                    cachedTotal += delta.get(JAVA_DOUBLE, 0);
+                    shadow[k] = now[k];
+                    sinceFull++;
+                }
+                return cachedTotal;
+            }
+        }
         uploadCoordinates(mol);
         check((int) invoke(ENERGY, handle, total, comps));
-        return total.get(JAVA_DOUBLE, 0);
+        cachedTotal = total.get(JAVA_DOUBLE, 0);
+        cachedOptions = options;
+        sinceFull = 0;
+        return cachedTotal;
+    }
+
+    private static double[] coordinatesOf(IAtomContainer mol) {
+        double[] now = new double[3 * mol.getAtomCount()];
+        for (IAtom a : mol.atoms()) {
+            javax.vecmath.Point3d p = a.getPoint3d();
+            int i = 3 * a.getIndex();
+            now[i] = p.x; now[i + 1] = p.y; now[i + 2] = p.z;
+        }
+        return now;
     }
 
     /** Addition (the reference has no gradient): dE/dx, [n][3], in the force field's energy unit per Angstrom. */
@@ -83,12 +126,7 @@ public final class GpuMMFF94Component extends EnergyComponent implements AutoClo
 
     private void uploadCoordinates(IAtomContainer mol) {
         int n = mol.getAtomCount(), changed = 0, last = -1;
-        double[] now = new double[3 * n];
-        for (IAtom a : mol.atoms()) {
-            javax.vecmath.Point3d p = a.getPoint3d();
-            int i = 3 * a.getIndex();
-            now[i] = p.x; now[i + 1] = p.y; now[i + 2] = p.z;
-        }
+        double[] now = coordinatesOf(mol);
         if (shadow != null) for (int k = 0; k < 3 * n; k++) if (now[k] != shadow[k]) { changed++; last = k; }
         if (shadow != null && changed == 0) return;
         if (shadow != null && changed == 1) {                                 // minimizer fast path: 8 bytes, not 24 n
@@ -116,7 +154,8 @@ public final class GpuMMFF94Component extends EnergyComponent implements AutoClo
         xyz = arena.allocate(JAVA_DOUBLE, 3L * n);
         total = arena.allocate(JAVA_DOUBLE);
         comps = arena.allocate(JAVA_DOUBLE, 7);
-        bound = mol; boundPairMap = pairMap; shadow = null;
+        delta = arena.allocate(JAVA_DOUBLE, 8);
+        bound = mol; boundPairMap = pairMap; shadow = null; cachedOptions = null;
     }
 
     private void check(int rc) {

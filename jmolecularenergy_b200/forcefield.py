@@ -127,6 +127,8 @@ class _GpuState:
         self.shadow: Optional[np.ndarray] = None
         self.options = None
         self.path = None
+        self.cached = None             # (options, components + total) of the last energy, for the incremental mode
+        self.since_full = 0            # incremental answers since the last full evaluation
 
     def check(self, rc: int) -> None:
         if rc != 0:
@@ -137,6 +139,7 @@ class _GpuState:
         if opt != self.options:
             self.check(self.L.jme_set_options(self.h, opt[0], opt[1], ENERGY_UNITS[opt[2]]))
             self.options = opt
+            self.cached = None
         if path != self.path:
             self.check(self.L.jme_set_path(self.h, PATHS[path]))
             self.path = path
@@ -149,6 +152,7 @@ class _GpuState:
             changed = np.flatnonzero(flat != self.shadow)
             if changed.size == 0:
                 return
+            self.cached = None         # (the incremental mode moves its one coordinate itself, before this is reached)
             if changed.size <= 3:
                 for k in changed.tolist():
                     self.check(self.L.jme_set_coord1(self.h, k // 3, k % 3, float(flat[k])))
@@ -156,6 +160,7 @@ class _GpuState:
                 return
         self.check(self.L.jme_set_coords(self.h, flat.ctypes.data, self.n))
         self.shadow = flat.copy()
+        self.cached = None
 
     def close(self) -> None:
         if self.h is not None and self.h.value:
@@ -206,6 +211,15 @@ class MMFF94(ForceField):
                   self.electrostaticComponent):                         # order of MMFF94.java:98
             self.addEnergyComponent(c)
         self.lastEvaluation: Dict[str, float] = {}
+        self.incremental = False
+
+    def setIncremental(self, on: bool) -> None:
+        """Opt in to incremental energies: when exactly ONE coordinate changed since the last ``calculateEnergy`` of a
+        container - which is what the reference's minimizers do between two calls (``GradientDescentMinimizer.java:
+        75-93``) - the answer is the previous energy plus ``jme_energy_delta`` (the moved atom's terms only, O(N))
+        instead of a full evaluation (two coordinates - the undo of a rejected trial plus the next trial - cost two deltas);
+        every 3 N such answers, and whenever anything else changed, a full evaluation resynchronises.  The unchanged minimizer loops get the speed-up through the unchanged ``calculateEnergy``."""
+        self.incremental = bool(on)
 
     # -- marshalling -------------------------------------------------------------------------
     def assignParameters(self, atomContainer: MolecularSystem) -> None:
@@ -233,6 +247,27 @@ class MMFF94(ForceField):
     def _evaluate(self, atomContainer: MolecularSystem, gradient: bool) -> Dict[str, object]:
         st = self._state(atomContainer)
         st.sync_options(self, self.path)
+        if self.incremental and not gradient and st.cached is not None and st.shadow is not None \
+                and st.since_full < 3 * st.n:
+            flat = np.ascontiguousarray(atomContainer.xyz, dtype=np.float64).reshape(-1)
+            changed = np.flatnonzero(flat != st.shadow) if flat.shape[0] == st.shadow.shape[0] else np.arange(2)
+            if changed.size == 0:
+                return dict(st.cached)
+            if changed.size <= 2:
+                # one coordinate moved - or two: the undo of a rejected trial and the next trial, which is what the
+                # reference's loops leave between two calls (GradientDescentMinimizer.java:83-93) - one delta each
+                out = dict(st.cached)
+                for k in changed.tolist():
+                    d = (C.c_double * 8)()
+                    st.check(st.L.jme_energy_delta(st.h, k // 3, k % 3, float(flat[k]), d))
+                    st.shadow[k] = flat[k]
+                    st.since_full += 1
+                    out["total"] += d[0]
+                    for j, name in enumerate(COMPONENTS):
+                        out[name] += d[1 + j]
+                st.cached = dict(out)
+                self.lastEvaluation = out
+                return out
         st.sync_coords(atomContainer.xyz)
         total = C.c_double()
         comps = np.zeros(7)
@@ -250,6 +285,8 @@ class MMFF94(ForceField):
         out["pairs"] = pe.value
         out["candidates"] = pc.value
         self.lastEvaluation = out
+        st.cached = {k: v for k, v in out.items() if k != "gradient"}
+        st.since_full = 0
         return out
 
     def calculateEnergy(self, atomContainer: MolecularSystem) -> float:
@@ -290,6 +327,7 @@ class MMFF94(ForceField):
         atomContainer.xyz[atom, axis] = value
         if st.shadow is not None:
             st.shadow[3 * atom + axis] = value
+        st.cached = None
         out = {"total": d[0]}
         for k, name in enumerate(COMPONENTS):
             out[name] = d[1 + k]

@@ -389,6 +389,44 @@ def test_incremental_minimizers_follow_the_full_evaluation_loops():
         assert abs(e1[-1] - f1) <= 1e-8 * max(1.0, abs(f1))       # the running energy of the incremental loop is the real one
 
 
+def test_incremental_force_field_behind_the_unchanged_minimizer():
+    """``MMFF94.setIncremental(True)``: the reference-style Python minimizer loop (one ``calculateEnergy`` after every
+    single-coordinate move) gets its energies from jme_energy_delta; same trajectory as with full evaluations, and a
+    change of more than one coordinate, of an option, or a gradient call falls back to a full evaluation."""
+    from jmolecularenergy_b200 import GradientDescentMinimizer, MMFF94, systems
+    runs = []
+    for inc in (False, True):
+        s = systems.water_box(6)
+        s.xyz += np.random.default_rng(3).normal(0, 0.05, s.xyz.shape)
+        ff = MMFF94(False)
+        ff.setIncremental(inc)
+        ff.assignParameters(s)
+        energies = []
+        m = GradientDescentMinimizer(ff)
+        m.setOnStepConsumer(lambda k, e: energies.append(e))
+        launches0 = ff.launchCount(s)
+        m.minimize(s, 3, 0.02, 1e-9)
+        runs.append((energies, s.xyz.copy(), ff.launchCount(s) - launches0))
+        full = MMFF94(False)
+        full.assignParameters(s)
+        assert abs(full.calculateEnergy(s) - ff.calculateEnergy(s)) <= 1e-9
+        # more than one coordinate moved: a full evaluation again
+        s.xyz[0] += 0.01
+        assert abs(full.calculateEnergy(s) - ff.calculateEnergy(s)) <= 1e-9
+        # one coordinate, other dielectric constant: the cache must not be used
+        s.xyz[1, 2] += 0.01
+        ff.setDielectricConstant(2.0)
+        full.setDielectricConstant(2.0)
+        assert abs(full.calculateEnergy(s) - ff.calculateEnergy(s)) <= 1e-9
+        full.release(s)
+        ff.release(s)
+    (e0, x0, l0), (e1, x1, l1) = runs
+    assert len(e0) == len(e1) and len(e0) >= 2
+    np.testing.assert_allclose(e1, e0, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(x1, x0, rtol=0, atol=1e-9)
+    assert l1 < l0                                                 # one small kernel per trial instead of an evaluation
+
+
 def test_gradient_descent_minimizer_matches_oracle_driven_loop(oracle):
     """The reference's GradientDescentMinimizer loop (restated in jmolecularenergy_b200/minimizer.py) driven
     by the GPU force field vs the same loop driven by the oracle energy: same accepted energies."""
