@@ -177,9 +177,12 @@ int jme_adam_minimize(jme_handle_t* h, int max_steps, double step_size, double t
  * jme_set_coord1) and returns delta[0] = change of the total, delta[1..7] = change of the seven components, in the
  * handle's energy unit.  Addition - the reference has nothing like it.
  * jme_set_incremental(h, 1) makes jme_gd_minimize / jme_adam_minimize use it for every trial move (one full evaluation
- * at the start only); the default (0) evaluates the full energy per trial like the reference. */
+ * at the start only); mode 2 runs the whole loop in one kernel - a cluster of eight thread blocks that keep the
+ * coordinates in shared memory and exchange their partial sums through distributed shared memory, no host round trip
+ * per trial - for systems of up to 8 192 atoms (larger ones run as mode 1); the default (0) evaluates the full energy
+ * per trial like the reference. */
 int jme_energy_delta(jme_handle_t* h, int64_t atom, int axis, double value, double* delta /*[8]*/);
-int jme_set_incremental(jme_handle_t* h, int on);
+int jme_set_incremental(jme_handle_t* h, int mode);
 
 /* ---- owner-mode exchange of a multi-GPU job over NVLink peer memory ----
  * One process per GPU, every rank owns chunk = jme_peer_chunk() consecutive atoms (by original index; the last

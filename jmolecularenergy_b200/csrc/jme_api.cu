@@ -96,7 +96,7 @@ struct jme_handle {
     double* h_delta = nullptr;     // pinned, mapped: [0] total, [1..7] components, [8] sequence number
     double* h_delta_dev = nullptr;
     uint64_t delta_seq = 0;
-    bool incremental = false;      // the native minimizer loops use jme_energy_delta instead of full evaluations
+    int incremental = 0;           // native minimizer loops: 0 full evaluations, 1 jme_energy_delta per trial, 2 the whole loop on the device
 
     // CUDA graphs of the all-pairs evaluation sequence {nonbonded | bonded} -> reduce (launch-bound small
     // systems): one per (gradient?, output buffer); rebuilt whenever anything baked into the kernel arguments changes
@@ -830,6 +830,106 @@ int jme_energy_gradient(jme_handle_t* h, double* total, double comps[JME_N_COMPO
 // The change of the seven components ([1..7]) and of the total ([0]) that moving ONE coordinate causes, and the move
 // itself (jme_delta.cuh): O(N) work.  delta: 8 doubles in the handle's energy unit.
 namespace {
+// device copies of the exclusion rows, partial / control words and the mapped result buffer of the delta path
+int ensure_delta_data(jme_handle_t* h) {
+    if (h->h_delta) return JME_OK;
+    int rc;
+    std::vector<long long> ptr(h->hs.excl_ptr.begin(), h->hs.excl_ptr.end());
+    std::vector<unsigned int> ent(h->hs.excl_ent.begin(), h->hs.excl_ent.end());
+    if ((rc = dev_upload(h, &h->d_dx_excl_ptr, ptr))) return rc;
+    if ((rc = dev_upload(h, &h->d_dx_excl_ent, ent))) return rc;
+    if ((rc = dev_alloc(h, &h->d_delta_part, 2 * (size_t)kDeltaMaxBlocks))) return rc;
+    if ((rc = dev_alloc(h, &h->d_delta_ctr, 1))) return rc;
+    JME_CUDA(h, cudaMemset(h->d_delta_ctr, 0, sizeof(unsigned int)));
+    if (cudaHostAlloc(&h->h_delta, 16 * sizeof(double), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(&h->h_delta_dev, h->h_delta, 0) != cudaSuccess)
+        return fail(h, JME_ERR_CUDA, "cudaHostAlloc (mapped) failed");
+    h->h_delta[8] = 0.0;
+    return JME_OK;
+}
+
+// The whole minimizer loop in one kernel (jme_delta.cuh: minimize_kernel).  The coordinates are on the device already and
+// e0 is their energy; on return xyz holds the final coordinates.
+int minimize_on_device(jme_handle_t* h, bool adam, int max_steps, double step_size, double threshold, double beta1, double beta2,
+                       double epsilon, double e0, double* xyz, int64_t* energy_calls, int* steps_done, double* step_energies,
+                       int capacity) {
+    int rc = ensure_plan(h);
+    if (rc) return rc;
+    if ((rc = ensure_delta_data(h))) return rc;
+    const size_t n = (size_t)h->hs.n;
+    const int cap = std::max(1, std::min(capacity, max_steps + 2));
+    double *d_grads = nullptr, *d_m = nullptr, *d_v = nullptr, *d_log = nullptr, *d_energy = nullptr;
+    int *d_t = nullptr, *d_steps = nullptr;
+    long long* d_calls = nullptr;
+    auto cleanup = [&]() {
+        for (void* q : {(void*)d_grads, (void*)d_m, (void*)d_v, (void*)d_log, (void*)d_energy, (void*)d_t, (void*)d_steps, (void*)d_calls})
+            if (q) cudaFree(q);
+    };
+    auto bail = [&](cudaError_t e, const char* what) { cleanup(); return fail(h, JME_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e)); };
+    cudaError_t ce;
+    const size_t nw = (size_t)kMinimizeCtas * 3 * n;          // per-CTA copies of the loop state
+    if ((ce = cudaMalloc(&d_grads, nw * sizeof(double))) != cudaSuccess) return bail(ce, "cudaMalloc");
+    if (adam) {
+        if ((ce = cudaMalloc(&d_m, nw * sizeof(double))) != cudaSuccess) return bail(ce, "cudaMalloc");
+        if ((ce = cudaMalloc(&d_v, nw * sizeof(double))) != cudaSuccess) return bail(ce, "cudaMalloc");
+        if ((ce = cudaMalloc(&d_t, nw * sizeof(int))) != cudaSuccess) return bail(ce, "cudaMalloc");
+    }
+    if ((ce = cudaMalloc(&d_log, (size_t)cap * sizeof(double))) != cudaSuccess) return bail(ce, "cudaMalloc");
+    if ((ce = cudaMalloc(&d_energy, sizeof(double))) != cudaSuccess) return bail(ce, "cudaMalloc");
+    if ((ce = cudaMalloc(&d_steps, sizeof(int))) != cudaSuccess) return bail(ce, "cudaMalloc");
+    if ((ce = cudaMalloc(&d_calls, sizeof(long long))) != cudaSuccess) return bail(ce, "cudaMalloc");
+    cudaMemsetAsync(d_log, 0, (size_t)cap * sizeof(double), h->stream);
+    MinimizeArgs A{};
+    A.S = h->ds;
+    A.x = h->d_x; A.y = h->d_y; A.z = h->d_z;
+    A.cutoff_on = h->cutoff > 0 ? 1 : 0;
+    A.excl_ptr = h->d_dx_excl_ptr; A.excl_ent = h->d_dx_excl_ent;
+    A.B = h->bt; A.slot_ptr = h->d_slot_ptr; A.slot_idx = h->d_slot_idx;
+    A.unit_num = h->unit == JME_KCAL_PER_MOL ? 1.0 : kUnitToJoule[JME_KCAL_PER_MOL];
+    A.unit_den = h->unit == JME_KCAL_PER_MOL ? 1.0 : kUnitToJoule[h->unit];
+    A.adam = adam ? 1 : 0;
+    A.max_steps = max_steps; A.step_size = step_size; A.threshold = threshold;
+    A.beta1 = beta1; A.beta2 = beta2; A.epsilon = epsilon;
+    A.e0 = e0;
+    A.grads = d_grads; A.adam_m = d_m; A.adam_v = d_v; A.adam_t = d_t;
+    A.log = d_log; A.capacity = cap;
+    A.out_calls = d_calls; A.out_steps = d_steps; A.out_energy = d_energy;
+    const size_t smem = 3 * n * sizeof(double);
+    if ((ce = cudaFuncSetAttribute(minimize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+        return bail(ce, "minimize_kernel shared memory");
+    {   // one cluster of kMinimizeCtas CTAs
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(kMinimizeCtas, 1, 1);
+        cfg.blockDim = dim3(kMinimizeThreads, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = h->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kMinimizeCtas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if ((ce = cudaLaunchKernelEx(&cfg, minimize_kernel, A)) != cudaSuccess) return bail(ce, "minimize_kernel launch");
+    }
+    ++h->launches;
+    if ((ce = cudaGetLastError()) != cudaSuccess) return bail(ce, "minimize_kernel launch");
+    h->cells.coords_changed();
+    std::vector<double> log((size_t)cap);
+    long long calls = 0;
+    int steps = 0;
+    cudaMemcpyAsync(log.data(), d_log, (size_t)cap * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(&calls, d_calls, sizeof(calls), cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(&steps, d_steps, sizeof(steps), cudaMemcpyDeviceToHost, h->stream);
+    if ((ce = cudaStreamSynchronize(h->stream)) != cudaSuccess) return bail(ce, "minimize_kernel");
+    cleanup();
+    if ((rc = jme_get_coords(h, xyz, (int64_t)n))) return rc;
+    if (step_energies) for (int k = 1; k <= steps && k < capacity && k < cap; ++k) step_energies[k] = log[(size_t)k];
+    if (energy_calls) *energy_calls = calls;
+    if (steps_done) *steps_done = steps;
+    return JME_OK;
+}
+}  // namespace
+
+namespace {
 struct PendingUndo { int64_t atom = -1; int axis = 0; double value = 0; };
 int energy_delta_impl(jme_handle_t* h, int64_t atom, int axis, double value, double* delta, const PendingUndo* undo);
 }  // namespace
@@ -847,19 +947,7 @@ int energy_delta_impl(jme_handle_t* h, int64_t atom, int axis, double value, dou
     JME_CUDA(h, cudaSetDevice(h->device));
     int rc = ensure_plan(h);                       // cutoff threshold, dielectric scale
     if (rc) return rc;
-    if (!h->h_delta) {
-        std::vector<long long> ptr(h->hs.excl_ptr.begin(), h->hs.excl_ptr.end());
-        std::vector<unsigned int> ent(h->hs.excl_ent.begin(), h->hs.excl_ent.end());
-        if ((rc = dev_upload(h, &h->d_dx_excl_ptr, ptr))) return rc;
-        if ((rc = dev_upload(h, &h->d_dx_excl_ent, ent))) return rc;
-        if ((rc = dev_alloc(h, &h->d_delta_part, 2 * (size_t)kDeltaMaxBlocks))) return rc;
-        if ((rc = dev_alloc(h, &h->d_delta_ctr, 1))) return rc;
-        JME_CUDA(h, cudaMemset(h->d_delta_ctr, 0, sizeof(unsigned int)));
-        if (cudaHostAlloc(&h->h_delta, 16 * sizeof(double), cudaHostAllocMapped) != cudaSuccess ||
-            cudaHostGetDevicePointer(&h->h_delta_dev, h->h_delta, 0) != cudaSuccess)
-            return fail(h, JME_ERR_CUDA, "cudaHostAlloc (mapped) failed");
-        h->h_delta[8] = 0.0;
-    }
+    if ((rc = ensure_delta_data(h))) return rc;
     DeltaArgs A{};
     A.S = h->ds;
     A.x = h->d_x; A.y = h->d_y; A.z = h->d_z;
@@ -896,9 +984,10 @@ int energy_delta_impl(jme_handle_t* h, int64_t atom, int axis, double value, dou
 }
 }  // namespace
 
-int jme_set_incremental(jme_handle_t* h, int on) {
+int jme_set_incremental(jme_handle_t* h, int mode) {
     if (!h) return JME_ERR_INVALID;
-    h->incremental = on != 0;
+    if (mode < 0 || mode > 2) return fail(h, JME_ERR_INVALID, "incremental mode: 0, 1 or 2");
+    h->incremental = mode;
     return JME_OK;
 }
 
@@ -933,6 +1022,9 @@ int jme_gd_minimize(jme_handle_t* h, int max_steps, double step_size, double thr
     if ((rc = energy(last_energy))) return rc;                     // :56
     int n_log = 0;
     if (step_energies && n_log < capacity) step_energies[n_log++] = last_energy;   // onStepConsumer(0, E)
+    if (h->incremental == 2 && h->world == 1 && n > 0 && n <= kMinimizeMaxAtoms)
+        return minimize_on_device(h, false, max_steps, step_size, threshold, 0, 0, 0, last_energy, xyz, energy_calls, steps_done,
+                                  step_energies, capacity);
     while (step < max_steps) {
         if (step != 0 && std::fabs(previous_step_energy - last_energy) <= threshold) break;   // :62-64
         previous_step_energy = last_energy;
@@ -1013,6 +1105,9 @@ int jme_adam_minimize(jme_handle_t* h, int max_steps, double step_size, double t
     if ((rc = energy(last_energy))) return rc;                     // :73
     int n_log = 0;
     if (step_energies && n_log < capacity) step_energies[n_log++] = last_energy;
+    if (h->incremental == 2 && h->world == 1 && n > 0 && n <= kMinimizeMaxAtoms)
+        return minimize_on_device(h, true, max_steps, step_size, threshold, beta1, beta2, epsilon, last_energy, xyz, energy_calls,
+                                  steps_done, step_energies, capacity);
     while (step < max_steps) {
         if (step != 0 && std::fabs(energy_per_step - last_energy) <= threshold) break;    // :78-80
         energy_per_step = last_energy;

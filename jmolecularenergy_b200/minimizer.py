@@ -99,17 +99,26 @@ class GradientDescentMinimizer(EnergyMinimizer):
                     self.onStepConsumer(self.step, lastEnergy)
 
 
+def _incremental_mode(incremental) -> int:
+    """False / 0: a full evaluation per trial (the reference's loop); True / 1: ``jme_energy_delta`` per trial;
+    "device" / 2: the whole loop in one kernel (``minimize_kernel``: systems of up to 8 192 atoms - larger ones are
+    run as mode 1)."""
+    if incremental in ("device", 2):
+        return 2
+    return 1 if incremental else 0
+
+
 class NativeGradientDescentMinimizer(EnergyMinimizer):
     """The same loop as :class:`GradientDescentMinimizer`, run inside ``libjme_b200.so`` (``jme_gd_minimize``): no
     per-call Python / ctypes overhead, which is what BASELINE config 4 (energy calls per second inside the
     optimizer) measures.  Constraints are not supported on this path.  ``incremental=True``: every trial move is
-    answered by ``jme_energy_delta`` (the energy change from the moved atom's terms only, O(N)) instead of a full
+    answered by ``jme_energy_delta``; ``incremental="device"``: the whole loop runs in one kernel - (the energy change from the moved atom's terms only, O(N)) instead of a full
     evaluation - same loop, same decisions up to the rounding of the differences."""
 
-    def __init__(self, forcefield, incremental: bool = False):
+    def __init__(self, forcefield, incremental=False):
         super().__init__()
         self.forcefield = forcefield
-        self.incremental = bool(incremental)
+        self.incremental = _incremental_mode(incremental)
         self.energyCalls = 0
         self.stepEnergies = []
 
@@ -122,7 +131,7 @@ class NativeGradientDescentMinimizer(EnergyMinimizer):
         xyz = np.ascontiguousarray(container.xyz, dtype=np.float64)
         calls, steps = C.c_int64(), C.c_int()
         log = np.zeros(maximumSteps + 2)
-        st.check(st.L.jme_set_incremental(st.h, 1 if self.incremental else 0))
+        st.check(st.L.jme_set_incremental(st.h, self.incremental))
         st.check(st.L.jme_gd_minimize(st.h, int(maximumSteps), float(stepSize), float(threshold),
                                       xyz.ctypes.data_as(C.POINTER(C.c_double)), C.byref(calls), C.byref(steps),
                                       log.ctypes.data_as(C.POINTER(C.c_double)), log.shape[0]))
@@ -161,7 +170,7 @@ class AdamMinimizer(EnergyMinimizer):
         super().__init__()
         self.forcefield = forceField
         self.beta1, self.beta2, self.epsilon = beta1, beta2, epsilon
-        self.incremental = bool(incremental)          # see NativeGradientDescentMinimizer
+        self.incremental = _incremental_mode(incremental)          # see NativeGradientDescentMinimizer
         self.energyCalls = 0
 
     def _energy(self, container) -> float:
@@ -220,7 +229,7 @@ class NativeAdamMinimizer(EnergyMinimizer):
         super().__init__()
         self.forcefield = forceField
         self.beta1, self.beta2, self.epsilon = beta1, beta2, epsilon
-        self.incremental = bool(incremental)          # see NativeGradientDescentMinimizer
+        self.incremental = _incremental_mode(incremental)          # see NativeGradientDescentMinimizer
         self.energyCalls = 0
         self.stepEnergies = []
 
@@ -233,7 +242,7 @@ class NativeAdamMinimizer(EnergyMinimizer):
         xyz = np.ascontiguousarray(container.xyz, dtype=np.float64)
         calls, steps = C.c_int64(), C.c_int()
         log = np.zeros(maximumSteps + 2)
-        st.check(st.L.jme_set_incremental(st.h, 1 if self.incremental else 0))
+        st.check(st.L.jme_set_incremental(st.h, self.incremental))
         st.check(st.L.jme_adam_minimize(st.h, int(maximumSteps), float(stepSize), float(threshold), float(self.beta1),
                                         float(self.beta2), float(self.epsilon), xyz.ctypes.data_as(C.POINTER(C.c_double)),
                                         C.byref(calls), C.byref(steps), log.ctypes.data_as(C.POINTER(C.c_double)),
