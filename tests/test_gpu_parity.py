@@ -368,13 +368,21 @@ def test_incremental_minimizers_follow_the_full_evaluation_loops():
     """The native minimizer loops with ``incremental=True`` (every trial answered by jme_energy_delta) against the same
     loops with a full evaluation per trial: same number of steps and energy calls, step energies equal to rounding."""
     from jmolecularenergy_b200 import MMFF94, NativeAdamMinimizer, NativeGradientDescentMinimizer, systems
-    for make in (lambda ff, inc: NativeGradientDescentMinimizer(ff, incremental=inc),
-                 lambda ff, inc: NativeAdamMinimizer(ff, 0.9, 0.999, 1e-8, incremental=inc)):
+    from jmolecularenergy_b200 import EnergyUnit
+    builders = [(lambda: systems.water_box(8), 0.0, EnergyUnit.KCAL_PER_MOL),
+                (lambda: load_golden("CO08A"), 0.0, EnergyUnit.KJ_PER_MOL),          # torsions, out-of-plane terms, 1-4 pairs
+                (lambda: systems.water_box(20), 5.0, EnergyUnit.KCAL_PER_MOL)]      # with a cutoff
+    makers = (lambda ff, inc: NativeGradientDescentMinimizer(ff, incremental=inc),
+              lambda ff, inc: NativeAdamMinimizer(ff, 0.9, 0.999, 1e-8, incremental=inc))
+    for build, cutoff, unit in builders:
+      for make in makers:
         runs = []
         for inc in (False, True, "device"):
-            s = systems.water_box(8)
+            s = build()
             s.xyz += np.random.default_rng(5).normal(0, 0.05, s.xyz.shape)
             ff = MMFF94(False)
+            ff.setCutoffDistance(cutoff)
+            ff.setEnergyUnit(unit)
             ff.assignParameters(s)
             m = make(ff, inc)
             m.minimize(s, 4, 0.02, 1e-9)
