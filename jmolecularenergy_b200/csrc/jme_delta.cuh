@@ -217,7 +217,6 @@ minimize_kernel(MinimizeArgs A) {
     __shared__ double s_red[kMinimizeThreads / 32][7];
     __shared__ double s_part[2][kMinimizeCtas][8];  // [trial parity][CTA][component]: every CTA's partial sums, in every CTA
     __shared__ double s_bc[4];                     // broadcast: [0] the move, [1] go on (1) / skip (0), [2] the accepted difference
-    __shared__ double s_delta;
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const int n_cta = (int)cluster.num_blocks(), cta = (int)cluster.block_rank();
@@ -238,7 +237,7 @@ minimize_kernel(MinimizeArgs A) {
     auto spos = [&](int k) { return Vec3{sx[k], sy[k], sz[k]}; };
     const BondedTerms& B = A.B;
 
-    // the energy change of moving coordinate (a, axis) to `value`, on every thread (block-wide)
+    // the energy change of moving coordinate (a, axis) to `value` (block- and cluster-wide work; the result on thread 0)
     auto delta_of = [&](int a, int axis, double value) -> double {
         const Vec3 p_old = spos(a);
         Vec3 p_new = p_old;
@@ -319,22 +318,21 @@ minimize_kernel(MinimizeArgs A) {
             }
         }
         cluster.sync();                                            // (also a barrier of this CTA; the table alternates with the
-        if (tid == 0) {                                            // trial, so one barrier per trial is enough)
-            double total = 0;
+        double total = 0;                                          // trial, so one barrier per trial is enough)
+        if (tid == 0) {                                            // only thread 0 needs the value: it takes the decision
             for (int k = 0; k < 7; ++k) {                          // components in the reference's order, converted one by one
                 double v = 0;
                 for (int r = 0; r < n_cta; ++r) v += s_part[par][r][k];
                 total += convert_unit(v, A.unit_num, A.unit_den);
             }
-            s_delta = total;
         }
-        __syncthreads();
-        return s_delta;
+        return total;
     };
     auto set_coord = [&](int a, int axis, double value) { (axis == 0 ? sx : (axis == 1 ? sy : sz))[a] = value; };
     auto get_coord = [&](int a, int axis) { return (axis == 0 ? sx : (axis == 1 ? sy : sz))[a]; };
 
     long long calls = 1;                                          // the caller's evaluation of e0
+    double g_next = tid == 0 ? grads[0] : 0.0;                    // thread 0 reads the slope of the NEXT trial during this one
     int step = 0;
     bool initialized = false;
     double last_energy = A.e0, previous = 0;
@@ -345,7 +343,9 @@ minimize_kernel(MinimizeArgs A) {
             for (int i = 0; i < 3; ++i) {
                 // thread 0 decides the trial (every thread could: the inputs are shared - but pow() once is enough)
                 if (tid == 0) {
-                    const double g = grads[3 * a + i];
+                    const double g = g_next;
+                    const int nxt = 3 * a + i + 1;
+                    g_next = grads[nxt < 3 * n ? nxt : 0];        // (index 0 again after the last one: the next sweep starts there)
                     double distance = 0;
                     double go = 1;
                     if (g == 0) {
