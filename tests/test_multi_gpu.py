@@ -1,5 +1,6 @@
-"""Multi-GPU parity on real NCCL (owner mode was only checked by eye): two ranks under torchrun, each
-compares its owned gradient rows and the job-wide energies with the CPU oracle.  Needs >= 2 visible GPUs
+"""Multi-GPU parity on real hardware (owner mode was only checked by eye): 2, 4 and 8 ranks under torchrun, each
+compares its owned gradient rows and the job-wide energies with the CPU oracle - through the NCCL collectives and through
+the exchange over NVLink peer memory (tests/mgpu_worker.py).  Needs >= 2 visible GPUs
 (`gpurun --gpus 2 -- python -m pytest tests/test_multi_gpu.py -m gpu`); skipped otherwise."""
 import os
 import socket
@@ -18,7 +19,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_owner_mode_under_torchrun_matches_the_oracle(world):
     import torch
     if torch.cuda.device_count() < world:
