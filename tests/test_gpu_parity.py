@@ -364,6 +364,30 @@ def test_energy_delta_equals_difference_of_full_evaluations(oracle):
             ff.release(s)
 
 
+def test_energy_delta_on_the_cell_paths():
+    """jme_energy_delta interleaved with full evaluations on both cutoff schemes (per-atom lists, cluster lists): a move
+    made by the delta kernel must invalidate the cell sort, and a move ACROSS a cell boundary or the cutoff of many
+    partners must still add up."""
+    from jmolecularenergy_b200 import MMFF94, systems
+    rng = np.random.default_rng(23)
+    for path in ("cells-lists", "cells-clusters"):
+        s = systems.ion_box(14)
+        ff = MMFF94(False, path=path)
+        ff.setCutoffDistance(9.0)
+        ff.assignParameters(s)
+        before = ff.calculateComponents(s)
+        for k in range(10):
+            a, ax = int(rng.integers(s.n_atoms)), int(rng.integers(3))
+            step = 6.0 if k % 3 == 0 else 0.3                     # every third move jumps over a cell (edge 4.5 A)
+            d = ff.energyChangeOfMove(s, a, ax, float(s.xyz[a, ax] + step))
+            after = ff.calculateComponents(s)
+            scale = max(1.0, abs(after["total"]))
+            for key in ("total", "vdw", "ele"):
+                assert abs(d[key] - (after[key] - before[key])) <= 5e-10 * scale, (path, k, key, d[key], after[key] - before[key])
+            before = after
+        ff.release(s)
+
+
 def test_incremental_minimizers_follow_the_full_evaluation_loops():
     """The native minimizer loops with ``incremental=True`` (every trial answered by jme_energy_delta) against the same
     loops with a full evaluation per trial: same number of steps and energy calls, step energies equal to rounding."""
