@@ -40,6 +40,11 @@ public final class GpuMMFF94Component extends EnergyComponent implements AutoClo
     private static final MethodHandle ENERGY = h("jme_energy", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
     private static final MethodHandle GRADIENT = h("jme_energy_gradient", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
     private static final MethodHandle DELTA = h("jme_energy_delta", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, JAVA_INT, JAVA_DOUBLE, ADDRESS));
+    private static final MethodHandle INCREMENTAL = h("jme_set_incremental", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
+    private static final MethodHandle GD = h("jme_gd_minimize", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_DOUBLE, JAVA_DOUBLE,
+            ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_INT));
+    private static final MethodHandle ADAM = h("jme_adam_minimize", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_DOUBLE, JAVA_DOUBLE,
+            JAVA_DOUBLE, JAVA_DOUBLE, JAVA_DOUBLE, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_INT));
     private static final MethodHandle LASTERR = h("jme_last_error", FunctionDescriptor.of(ADDRESS, ADDRESS));
     private static final MethodHandle CREATEERR = h("jme_last_create_error", FunctionDescriptor.of(ADDRESS));
 
@@ -121,6 +126,36 @@ public final class GpuMMFF94Component extends EnergyComponent implements AutoClo
             MemorySegment g = tmp.allocate(JAVA_DOUBLE, 3L * mol.getAtomCount());
             check((int) invoke(GRADIENT, handle, total, comps, g));
             return g.toArray(JAVA_DOUBLE);
+        }
+    }
+
+    /**
+     * The reference's minimizer loops run natively (jme_gd_minimize / jme_adam_minimize: GradientDescentMinimizer.java:
+     * 49-105, AdamMinimizer.java:62-120 restated, no constraint): mode 0 = a full evaluation per trial like the Java
+     * loops, 1 = jme_energy_delta per trial, 2 = the whole loop in one kernel (up to 8 192 atoms).  The container's
+     * coordinates are updated; returns the energy after every step (index 0: the initial energy), as onStepConsumer
+     * would have received them.  beta1 < 0 selects gradient descent, otherwise Adam with (beta1, beta2, epsilon).
+     */
+    public double[] minimizeNatively(IAtomContainer mol, int mode, int maxSteps, double stepSize, double threshold,
+                                     double beta1, double beta2, double epsilon) {
+        calculateEnergy(mol);                                                 // binds, marshals, uploads
+        int n = mol.getAtomCount();
+        try (Arena tmp = Arena.ofConfined()) {
+            MemorySegment xyzInOut = tmp.allocate(JAVA_DOUBLE, 3L * n);
+            MemorySegment.copy(coordinatesOf(mol), 0, xyzInOut, JAVA_DOUBLE, 0, 3 * n);
+            MemorySegment calls = tmp.allocate(JAVA_LONG), steps = tmp.allocate(JAVA_INT);
+            MemorySegment log = tmp.allocate(JAVA_DOUBLE, maxSteps + 2L);
+            check((int) invoke(INCREMENTAL, handle, mode));
+            if (beta1 < 0) check((int) invoke(GD, handle, maxSteps, stepSize, threshold, xyzInOut, calls, steps, log, maxSteps + 2));
+            else check((int) invoke(ADAM, handle, maxSteps, stepSize, threshold, beta1, beta2, epsilon, xyzInOut, calls, steps, log, maxSteps + 2));
+            double[] out = xyzInOut.toArray(JAVA_DOUBLE);
+            for (IAtom a : mol.atoms()) {
+                int i = 3 * a.getIndex();
+                a.getPoint3d().set(out[i], out[i + 1], out[i + 2]);
+            }
+            shadow = out;                                                      // what the device holds now
+            cachedOptions = null;
+            return log.asSlice(0, 8L * (steps.get(JAVA_INT, 0) + 1)).toArray(JAVA_DOUBLE);
         }
     }
 
