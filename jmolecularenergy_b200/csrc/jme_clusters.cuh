@@ -153,7 +153,7 @@ __device__ __forceinline__ void st_cs_if64(bool pred, unsigned long long base, u
                  ::"r"((unsigned int)pred), "r"(index), "l"(base), "r"(v.x), "r"(v.y) : "memory");
 }
 
-constexpr int kClListMinBlocks = 3;   // 85 registers per thread: no spills
+constexpr int kClListMinBlocks = 4;   // measured: 2 / 3 / 4 resident CTAs (102 / 80 / 64 registers) build the 10^6-ion lists in 0.76 / 0.69 / 0.68 ms, 5 (48 registers, spills) in 0.78
 
 // shared-memory scratch of one list-building warp (1 604 bytes)
 struct ClBuildSmem {
